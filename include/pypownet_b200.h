@@ -1,0 +1,172 @@
+/* pypownet_b200 -- C ABI of the B200-native batched power-grid step path.
+ *
+ * Drop-in boundary for the per-timestep hot path of pypownet (reference @ /root/reference):
+ *   RunEnv.step / simulate / process_game_over      pypownet/environment.py:848-888
+ *   Game.step, apply_action, _verify_illegal_action,
+ *   load_entries_from_next_timestep,
+ *   _compute_loadflow_cascading, process_game_over   pypownet/game.py:405-501, 503-589, 591-753, 762-885, 887-943
+ *   Grid.compute_loadflow + the four pypower.api
+ *   calls it makes (runpf / rundcpf)                 pypownet/grid.py:62-65, 140-264
+ *   Grid.extract_flows_a, load_timestep_injections,
+ *   apply_topology, export_to_observation            pypownet/grid.py:112-138, 273-311, 360-423, 496-566
+ *   Observation.as_array layout                      pypownet/environment.py:451-466, 511-517, 583-595
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types.  Every function returns 0 on success or a
+ * negative PPN_E_* code; ppn_last_error() gives the message.  Pointers named *_dev are device pointers on the
+ * handle's GPU, *_host are host pointers.  The caller owns every buffer it passes; the library owns the env
+ * state.  Work is enqueued on the CUDA stream passed as `stream` (a cudaStream_t cast to void*, NULL = default
+ * stream); calls on one handle must be serialised by the caller.  In-step "exceptions" of the reference
+ * (game.py:861-885 returns exception INSTANCES) are returned as per-env integer flags.
+ */
+#ifndef PYPOWNET_B200_H
+#define PYPOWNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPN_OK 0
+#define PPN_E_INVALID (-1)   /* bad argument / malformed case */
+#define PPN_E_CUDA (-2)      /* CUDA runtime error */
+#define PPN_E_STATE (-3)     /* call order (e.g. step before load_chronics/reset) */
+#define PPN_E_UNSUPPORTED (-4)
+
+/* per-env flag codes (replace the exception instances of game.py:861-885 / environment.py:14-35) */
+#define PPN_FLAG_NONE 0
+#define PPN_FLAG_ILLEGAL_ACTION 1        /* IllegalActionException  (step still played with the corrected action) */
+#define PPN_FLAG_DIVERGING_LOADFLOW 2    /* DivergingLoadflowException, done */
+#define PPN_FLAG_TOO_MANY_LOADS_CUT 3    /* TooManyConsumptionsCut, done */
+#define PPN_FLAG_TOO_MANY_PRODS_CUT 4    /* TooManyProductionsCut, done */
+
+/* Grid family: the MATPOWER-format case of Grid.__init__ (grid.py:40-93) in struct-of-arrays form.
+ * 2*n_sub buses: bus s is node 0 of substation s, bus s+n_sub its artificial '666' sister (node 1). */
+typedef struct ppn_case {
+    int32_t n_sub, n_gen, n_load, n_line;
+    double base_mva;
+    const int32_t* sub_ids;       /* [n_sub]  external substation ids (observation tail only) */
+    const int32_t* gen_sub;       /* [n_gen]  substation index of each generator, strictly ascending */
+    const int32_t* load_sub;      /* [n_load] substation index of each load, strictly ascending */
+    const int32_t* line_or_sub;   /* [n_line] */
+    const int32_t* line_ex_sub;   /* [n_line] */
+    const double* line_r;         /* [n_line] p.u. */
+    const double* line_x;
+    const double* line_b;         /* total line charging */
+    const double* line_tap;       /* off-nominal ratio, 0 means 1 (makeYbus) */
+    const uint8_t* line_status0;  /* [n_line] initial service status */
+    const double* bus_gs;         /* [2*n_sub] MW at 1 p.u. */
+    const double* bus_bs;         /* [2*n_sub] MVAr at 1 p.u. */
+    const double* bus_basekv;     /* [2*n_sub] */
+    const double* bus_vm0;        /* [2*n_sub] initial magnitudes, p.u. */
+    const double* bus_va0;        /* [2*n_sub] initial angles, DEGREES (bus[:, VA]) */
+    const double* gen_qmin;       /* [n_gen] */
+    const double* gen_qmax;       /* [n_gen] */
+    int32_t slack_sub;            /* substation whose node-0 bus is type 3 in the case file (grid.py:74) */
+    const double* thermal_limits; /* [n_line] A; the first chronic's imaps (game.py:301-304) */
+} ppn_case;
+
+/* configuration.yaml + RunEnv arguments (game.py:263-298, parameters.py:89-153) */
+typedef struct ppn_config {
+    int32_t dc;                          /* loadflow_mode == DC */
+    double hard_overflow_coefficient;    /* 1e9 when without_overflow_cutoff */
+    int32_t n_timesteps_hard_overflow_is_broken;
+    double n_timesteps_consecutive_soft_overflow_breaks; /* 1e12 when without_overflow_cutoff */
+    int32_t n_timesteps_soft_overflow_is_broken;
+    int32_t n_timesteps_horizon_maintenance;
+    int32_t max_number_prods_game_over;
+    int32_t max_number_loads_game_over;
+    int32_t n_timesteps_actionned_line_reactionable;
+    int32_t n_timesteps_actionned_node_reactionable;
+    int32_t max_number_actionned_substations;
+    int32_t max_number_actionned_lines;
+    int32_t max_number_actionned_total;
+    int32_t hard_game_over;              /* game_over_mode == 'hard' */
+    int32_t loop_mode;                   /* 0 natural, 1 random (counter-based hash, not numpy's stream), 2 fixed */
+    double pf_tol;                       /* 1e-6  (grid.py:63) */
+    int32_t pf_max_it;                   /* 25    (grid.py:63) */
+    double reward_constant;              /* `constant` of the shipped CustomRewardSignal (14 / 30 / 118) */
+    uint64_t seed;                       /* loop_mode 1 only */
+    int32_t threads_per_env;             /* 0 = automatic (32 for small grids); 32, 64 or 128 */
+} ppn_config;
+
+/* One chronic (chronic.py:174-246): float32 tables with n_rows rows, planned tables ALREADY shifted by one row. */
+typedef struct ppn_chronic {
+    int32_t n_rows;
+    const float* prods_p;          /* [n_rows, n_gen] */
+    const float* prods_v;          /* [n_rows, n_gen]  kV, <= 0 means generator off */
+    const float* loads_p;          /* [n_rows, n_load] */
+    const float* loads_q;
+    const float* prods_p_planned;
+    const float* prods_v_planned;
+    const float* loads_p_planned;
+    const float* loads_q_planned;
+    const float* maintenance;      /* [n_rows, n_line] integer-valued durations */
+    const float* hazards;          /* [n_rows, n_line] */
+    const int32_t* ids;            /* [n_rows] simu ids (unique) */
+    const int32_t* datetimes;      /* [n_rows, 6] year month day hour minute second */
+} ppn_chronic;
+
+typedef struct ppn_env ppn_env;
+
+/* state fields for ppn_get_state / ppn_set_state (device buffers, row-major [n_envs, width]) */
+#define PPN_STATE_VM 0            /* double [2*n_sub] */
+#define PPN_STATE_VA 1            /* double [2*n_sub] degrees */
+#define PPN_STATE_TOPOLOGY 2      /* uint8  [n_gen+n_load+3*n_line]: prods|loads|lines or|lines ex node bits, line status */
+#define PPN_STATE_COUNTERS 3      /* int32  [3*n_line+n_sub]: reconnectable|line reactionable|soft-overflow count|node reactionable */
+#define PPN_STATE_CURSOR 4        /* int32  [4]: chronic index, row (-1 none yet, -2 just switched), next chronic, rng counter */
+
+int ppn_create(const ppn_case* grid, const ppn_config* cfg, int n_envs, int device, ppn_env** out);
+int ppn_load_chronics(ppn_env* env, int n_chronics, const ppn_chronic* host_tables);
+
+/* Game.__init__ for every env (game.py:296-340): pristine grid, chronic chronic_idx[e] (NULL: 0), first row
+ * played row0[e] (NULL: 0), first load-flow cascade.  obs_dev (may be NULL) receives the dynamic observation prefix. */
+int ppn_reset(ppn_env* env, const int32_t* chronic_idx_host, const int32_t* row0_host, double* obs_dev, void* stream);
+
+/* RunEnv.step for every env (environment.py:848-866).  act_dev uint8 [n_envs, action_length]; obs_dev double
+ * [n_envs, obs_stride] or NULL (only the dynamic prefix, obs_dynamic_length values per row, is written; rows of
+ * `done` envs are left untouched unless auto_reset); reward_dev double [n_envs, 5] (the shipped five-term reward);
+ * done_dev uint8 [n_envs]; flag_dev int32 [n_envs]; illegal_dev uint8 [n_envs, 1+2*n_line+n_sub] or NULL:
+ * has_too_much_activations | illegal reconnections | on-cooldown line switches | on-cooldown substations.
+ * auto_reset != 0: envs that are done immediately run process_game_over (game.py:762-780) and their obs row
+ * receives the post-reset observation (Runner.step semantics, runner.py:84-87). */
+int ppn_step(ppn_env* env, const uint8_t* act_dev, double* obs_dev, int64_t obs_stride, double* reward_dev,
+             uint8_t* done_dev, int32_t* flag_dev, uint8_t* illegal_dev, int auto_reset, void* stream);
+
+/* RunEnv.simulate (environment.py:868-884, game.py:887-943) for n_candidates actions per env, no state commit.
+ * act_dev [n_envs, n_candidates, action_length]; outputs have n_envs*n_candidates rows. */
+int ppn_simulate(ppn_env* env, int n_candidates, const uint8_t* act_dev, double* obs_dev, int64_t obs_stride,
+                 double* reward_dev, uint8_t* done_dev, int32_t* flag_dev, uint8_t* illegal_dev, void* stream);
+
+/* RunEnv.process_game_over (environment.py:886-888) for envs with mask_dev[e] != 0 (NULL: all). */
+int ppn_process_game_over(ppn_env* env, const uint8_t* mask_dev, double* obs_dev, int64_t obs_stride, void* stream);
+
+/* Game.is_action_valid (game.py:755-760): valid_dev uint8 [n_envs]. */
+int ppn_action_valid(ppn_env* env, const uint8_t* act_dev, uint8_t* valid_dev, void* stream);
+
+/* Host-buffer form of ppn_step: copies act_host to the GPU, steps, copies results back and synchronises. */
+int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_host, int64_t obs_stride, double* reward_host,
+                  uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset);
+
+int ppn_get_state(ppn_env* env, int field, void* out_dev);
+int ppn_set_state(ppn_env* env, int field, const void* in_dev);
+/* static tail of Observation.as_array (environment.py:583-595), obs_length - obs_dynamic_length doubles, host */
+int ppn_observation_static(ppn_env* env, double* out_host);
+
+int ppn_n_envs(const ppn_env* env);
+int ppn_action_length(const ppn_env* env);
+int ppn_obs_length(const ppn_env* env);
+int ppn_obs_dynamic_length(const ppn_env* env);
+int ppn_device(const ppn_env* env);
+/* number of kernel launches issued by this handle so far, and cumulative device counters:
+ * out_host[0] load-flows, [1] fast-decoupled iterations, [2] env steps, [3] game-over resets, [4] max cascade depth,
+ * [5] kernel launches, [6] shared-memory bytes per env, [7] threads per env */
+int ppn_get_counters(ppn_env* env, int64_t* out_host /* [8] */);
+const char* ppn_last_error(const ppn_env* env);
+const char* ppn_build_info(void);
+void ppn_destroy(ppn_env* env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYPOWNET_B200_H */

@@ -26,9 +26,15 @@ the reference's own tests (slack Pg 123.370285 MW at tests/test_core.py:351-372,
 sequence at tests/test_core.py:917-934).  PYPOWER itself is not installable here, so agreement finer than the
 reference's own test tolerances (1e-3 MW) is agreement with the restated PYPOWER, not with the original wheel.
 
-One deliberate, documented normalisation: a load-flow on a grid that has an island without the reference bus is
-reported as diverging by an explicit connectivity test.  The reference gets there through a singular B' (splu
-raises -> grid.py:230) or a non-converging iteration; either way step() returns DivergingLoadflowException.
+One deliberate, documented normalisation: a load-flow on a grid with a multi-bus component that does not contain
+the reference bus ("not connexe") is reported as diverging by an explicit connectivity test.  In exact arithmetic
+B' of such a component is singular; the reference hands it to SuperLU (scipy splu through PYPOWER), which either
+reports "Factor is exactly singular" (-> grid.py:230 -> DivergingLoadflowException 'The grid is not connexe') or
+leaves a rounding-sized last pivot (~1e-16), in which case the component's common-mode update is (its net
+mismatch)/1e-16 and the iteration fails to converge unless the pocket carries no injection at all.  Which of the
+two happens depends on whether fl(b*fl(1/b)) == 1 for the pocket's line susceptances, i.e. on rounding inside
+SuperLU, not on the physics; so step() returns DivergingLoadflowException for every such grid, which is what the
+reference's own message says it means.  Measured deviation: see DESIGN.md ("floating pockets").
 """
 import numpy as np
 import scipy.linalg
@@ -298,6 +304,10 @@ class FlatEnv(object):
                 break
             reach = new
         if not reach.all():
+            # rundcpf on such a grid returns NaN/garbage that grid.py:260 adopts before raising; the only part of it
+            # that survives the reset that follows is the zeroing of out-of-service generators (runpf tail)
+            self.gen_pg[~gs] = 0
+            self.gen_qg[~gs] = 0
             return True
         if len(pvpq) == 0 or (len(pq) == 0 and not self.cfg.dc):
             return True                                                 # ValueError (norm of empty) -> grid.py:230

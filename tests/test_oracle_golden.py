@@ -1,0 +1,73 @@
+"""The CPU oracle (oracle/flat.py) against the fixtures recorded from the unmodified reference package
+(tools/make_golden.py), plus the known-answer values of the reference's own tests."""
+import numpy as np
+import pytest
+
+from golden_util import Fixture, fixture_names
+from oracle.flat import FlatEnv, Config
+
+TOL = 1e-9          # reference (scipy.sparse SuperLU) vs oracle (dense LAPACK): observed <= 4e-11
+
+
+def make_env(fx):
+    cfg = Config(fx.config, game_over_mode=fx.mode, reward_constant=fx.reward_constant, n_sub=fx.case.n_sub)
+    return FlatEnv(fx.case, cfg, fx.chronics)
+
+
+@pytest.mark.parametrize('name', fixture_names())
+def test_oracle_reproduces_reference_trajectory(name):
+    fx = Fixture(name)
+    env = make_env(fx)
+    assert np.max(np.abs(env.observation() - fx.obs0)) < TOL
+    nd = fx.case.obs_dynamic_length
+    for t in range(len(fx.actions)):
+        if fx.has_sim:
+            o, r, d, f, _ = env.simulate(fx.sim_actions[t])
+            assert (bool(d), int(f)) == (bool(fx.sim_done[t]), int(fx.sim_flag[t])), 'simulate %d' % t
+            if not d:
+                assert np.max(np.abs(o - fx.sim_obs[t][:nd])) < TOL, 'simulate %d' % t
+            if fx.default_reward:
+                assert np.max(np.abs(r - fx.sim_reward[t])) < TOL
+        o, r, d, f, _ = env.step(fx.actions[t])
+        assert (bool(d), int(f)) == (bool(fx.done[t]), int(fx.flag[t])), 'step %d' % t
+        if not d:
+            assert np.max(np.abs(o - fx.obs[t][:nd])) < TOL, 'step %d' % t
+        if fx.default_reward:
+            assert np.max(np.abs(r - fx.reward[t])) < TOL, 'step %d' % t
+        if d:
+            o = env.process_game_over()
+            assert np.max(np.abs(o - fx.reset_obs[t][:nd])) < TOL, 'reset %d' % t
+    assert np.max(np.abs(env.observation_static() - fx.obs0[nd:])) == 0
+
+
+def test_known_answers_of_the_reference_suite():
+    """/root/reference/tests/test_core.py:351-372 (slack production after the load-flow at t=1,2,3, 1e-3 MW) and
+    :551-603 (losses), on the reference's own test environment default14_for_tests, do-nothing agent."""
+    fx = Fixture('d14_tests_basic')
+    env = make_env(fx)
+    G, L = fx.case.n_gen, fx.case.n_load
+    expected_slack = [123.370285, 104.072556, 134.51176]
+    for t in range(3):
+        o, r, d, f, _ = env.step(np.zeros(fx.case.action_length, dtype=np.uint8))
+        assert not d and f == 0
+        prods = o[4 * L:4 * L + G]
+        assert abs(prods[0] - expected_slack[t]) < 1e-3
+        # the fixture (reference run) and the published constant agree as well
+        assert abs(fx.obs[t][4 * L] - expected_slack[t]) < 1e-3
+    assert np.all(prods[[2, 3]] == 0)           # gens 3 and 6 are off at t=3 (test_core.py:366-369)
+
+
+def test_hard_overflow_ampere_sequence():
+    """/root/reference/tests/test_core.py:917-934: line 6 current, do-nothing, first steps of the hard-overflow
+    environment: [244, 210, 223, 214, 214, 237, 244, 286, 322] then the line trips (limit 200 x coef 1.5)."""
+    fx = Fixture('d14_tests_hard_overflow')
+    env = make_env(fx)
+    G, L, N = fx.case.n_gen, fx.case.n_load, fx.case.n_line
+    off = 4 * L + 4 * G + 2 * N
+    seen = []
+    for t in range(9):
+        o, r, d, f, _ = env.step(np.zeros(fx.case.action_length, dtype=np.uint8))
+        assert not d
+        seen.append(int(o[off + 6]))
+    assert seen[:8] == [244, 210, 223, 214, 214, 237, 244, 286]
+    assert seen[8] == 0 and o[off + N + 6] == 0          # 322 A > 300 A: tripped within the step
