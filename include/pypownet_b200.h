@@ -62,6 +62,11 @@ typedef struct ppn_case {
     const double* bus_va0;        /* [2*n_sub] initial angles, DEGREES (bus[:, VA]) */
     const double* gen_qmin;       /* [n_gen] */
     const double* gen_qmax;       /* [n_gen] */
+    const double* gen_pg0;        /* [n_gen] case-file PG, QG, VG: the state before the first chronic row is loaded */
+    const double* gen_qg0;
+    const double* gen_vg0;
+    const double* load_pd0;       /* [n_load] case-file PD, QD of the load buses */
+    const double* load_qd0;
     int32_t slack_sub;            /* substation whose node-0 bus is type 3 in the case file (grid.py:74) */
     const double* thermal_limits; /* [n_line] A; the first chronic's imaps (game.py:301-304) */
 } ppn_case;
@@ -87,7 +92,7 @@ typedef struct ppn_config {
     int32_t pf_max_it;                   /* 25    (grid.py:63) */
     double reward_constant;              /* `constant` of the shipped CustomRewardSignal (14 / 30 / 118) */
     uint64_t seed;                       /* loop_mode 1 only */
-    int32_t threads_per_env;             /* 0 = automatic (32 for small grids); 32, 64 or 128 */
+    int32_t threads_per_env;             /* 0 = automatic (one warp per env up to 64 buses, else one CTA of 256); 32, 128 or 256 */
 } ppn_config;
 
 /* One chronic (chronic.py:174-246): float32 tables with n_rows rows, planned tables ALREADY shifted by one row. */
@@ -109,19 +114,21 @@ typedef struct ppn_chronic {
 
 typedef struct ppn_env ppn_env;
 
-/* state fields for ppn_get_state / ppn_set_state (device buffers, row-major [n_envs, width]) */
-#define PPN_STATE_VM 0            /* double [2*n_sub] */
-#define PPN_STATE_VA 1            /* double [2*n_sub] degrees */
-#define PPN_STATE_TOPOLOGY 2      /* uint8  [n_gen+n_load+3*n_line]: prods|loads|lines or|lines ex node bits, line status */
-#define PPN_STATE_COUNTERS 3      /* int32  [3*n_line+n_sub]: reconnectable|line reactionable|soft-overflow count|node reactionable */
-#define PPN_STATE_CURSOR 4        /* int32  [4]: chronic index, row (-1 none yet, -2 just switched), next chronic, rng counter */
+/* state fields for ppn_get_state / ppn_set_state (device buffers, row-major [n_envs, width], see ppn_state_width) */
+#define PPN_STATE_REAL 0      /* double: Vm[2S] | Va[2S] degrees | load P[L] | load Q[L] | gen Pg[G] | gen Qg[G] | gen Vg[G] */
+#define PPN_STATE_TOPOLOGY 1  /* uint8 : prods node[G] | loads node[L] | lines or node[N] | lines ex node[N] | line status[N] | gen status[G] */
+#define PPN_STATE_COUNTERS 2  /* int32 : reconnectable[N] | line reactionable[N] | soft-overflow count[N] | node reactionable[S] |
+                                         cursor[4] = chronic index, row (-1 none yet, -2 just switched), next chronic, rng counter */
 
 int ppn_create(const ppn_case* grid, const ppn_config* cfg, int n_envs, int device, ppn_env** out);
 int ppn_load_chronics(ppn_env* env, int n_chronics, const ppn_chronic* host_tables);
 
 /* Game.__init__ for every env (game.py:296-340): pristine grid, chronic chronic_idx[e] (NULL: 0), first row
- * played row0[e] (NULL: 0), first load-flow cascade.  obs_dev (may be NULL) receives the dynamic observation prefix. */
-int ppn_reset(ppn_env* env, const int32_t* chronic_idx_host, const int32_t* row0_host, double* obs_dev, void* stream);
+ * played row0[e] (NULL: 0), first load-flow cascade.  obs_dev (may be NULL) receives the dynamic observation prefix,
+ * flag_dev (may be NULL) PPN_FLAG_DIVERGING_LOADFLOW where that first cascade diverged -- the reference raises from
+ * the constructor there (game.py:340); a batch cannot, so such envs immediately run process_game_over. */
+int ppn_reset(ppn_env* env, const int32_t* chronic_idx_host, const int32_t* row0_host, double* obs_dev,
+              int64_t obs_stride, int32_t* flag_dev, void* stream);
 
 /* RunEnv.step for every env (environment.py:848-866).  act_dev uint8 [n_envs, action_length]; obs_dev double
  * [n_envs, obs_stride] or NULL (only the dynamic prefix, obs_dynamic_length values per row, is written; rows of
@@ -148,8 +155,9 @@ int ppn_action_valid(ppn_env* env, const uint8_t* act_dev, uint8_t* valid_dev, v
 int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_host, int64_t obs_stride, double* reward_host,
                   uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset);
 
-int ppn_get_state(ppn_env* env, int field, void* out_dev);
-int ppn_set_state(ppn_env* env, int field, const void* in_dev);
+int ppn_state_width(const ppn_env* env, int field);   /* elements per env of a PPN_STATE_* field */
+int ppn_get_state(ppn_env* env, int field, void* out_dev, void* stream);
+int ppn_set_state(ppn_env* env, int field, const void* in_dev, void* stream);
 /* static tail of Observation.as_array (environment.py:583-595), obs_length - obs_dynamic_length doubles, host */
 int ppn_observation_static(ppn_env* env, double* out_host);
 

@@ -71,7 +71,7 @@ class Config(object):
 
 
 class FlatEnv(object):
-    def __init__(self, case, config, chronics, start_id=0, thermal_limits=None):
+    def __init__(self, case, config, chronics, start_id=0, thermal_limits=None, start_row=0):
         self.c, self.cfg, self.chronics = case, config, chronics
         c = case
         S = c.n_sub
@@ -108,14 +108,19 @@ class FlatEnv(object):
         self.t_line_react = np.zeros(self.N)
         self.t_node_react = np.zeros(S)
         self.soft_count = np.zeros(self.N)
-        self.row = None                                                 # index in the current chronic (None: none yet)
+        # index in the current chronic (None: none yet).  start_row > 0 is the batched harness' way of starting
+        # envs at different offsets: as if row start_row-1 had just been played on the pristine grid
+        self.row = None if start_row == 0 else start_row - 1
         self.entries_row = None                                         # row of `current_timestep_entries`
         self.entries_chronic = None
         self.last_depth = 0
         self.n_loadflows = 0
-        # Game.__init__: first row + cascade (game.py:339-340); divergence here raises in the reference
+        # Game.__init__: first row + cascade (game.py:339-340); divergence here raises in the reference.  A batch
+        # cannot raise per env: it runs process_game_over instead (include/pypownet_b200.h, ppn_reset)
         self._load_next_timestep(False)
-        self._cascade()
+        self.init_diverged = self._cascade()
+        if self.init_diverged:
+            self.process_game_over()
 
     # ----------------------------------------------------------------------------------------------- chronic cursor
     def _take_next_chronic(self):

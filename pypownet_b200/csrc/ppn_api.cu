@@ -1,0 +1,564 @@
+// C ABI of the batched pypownet step path (include/pypownet_b200.h): handle management, upload of the grid family and
+// of the chronic tables, and the entry points that enqueue the fused step kernel (ppn_kernels.cu).
+// Everything numerical happens on the device; there is no CPU fallback behind these calls.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <complex>
+
+#include "../../include/pypownet_b200.h"
+#include "ppn_device.cuh"
+
+extern "C" int ppn_launch_step(const PpnDevCase* c, const PpnDevChronics* ch, const PpnDevCfg* cfg, const PpnDevState* st,
+                               const PpnStepArgs* args, int tpe, int envs_per_block, int env_smem_bytes,
+                               cudaStream_t stream);
+
+struct ppn_env {
+    int device = 0;
+    int B = 0;
+    int S = 0, G = 0, L = 0, N = 0, NB = 0, A = 0, OBS = 0, OBSD = 0;
+    PpnDevCase dc{};
+    PpnDevChronics dch{};
+    PpnDevCfg dcfg{};
+    PpnDevState st{};
+    bool chronics_loaded = false, initialised = false;
+    int tpe = 32, envs_per_block = 4, env_smem_bytes = 0, mat_cap = 0;
+    double* ws = nullptr;
+    long long ws_stride = 0, ws_rows = 0;
+    int horizon = 20;
+    unsigned long long* stats = nullptr;
+    long long launches = 0;
+    std::vector<void*> allocs;
+    std::vector<double> obs_static;
+    std::vector<int> chronic_rows;
+    // pinned staging for the host-buffer entry point
+    uint8_t* h_act = nullptr; uint8_t* d_act = nullptr;
+    double* h_obs = nullptr; double* d_obs = nullptr;
+    double* h_reward = nullptr; double* d_reward = nullptr;
+    uint8_t* h_done = nullptr; uint8_t* d_done = nullptr;
+    int32_t* h_flag = nullptr; int32_t* d_flag = nullptr;
+    uint8_t* h_ill = nullptr; uint8_t* d_ill = nullptr;
+    int32_t* d_init = nullptr;   // [2B] chronic idx | row0
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+static int fail(ppn_env* e, int code, const std::string& msg) {
+    if (e) e->err = msg;
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(env, PPN_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+template <typename T> static T* upload(ppn_env* env, const std::vector<T>& v, cudaError_t* err) {
+    T* d = nullptr;
+    size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+    *err = cudaMalloc(&d, bytes);
+    if (*err != cudaSuccess) return nullptr;
+    env->allocs.push_back(d);
+    if (v.size()) *err = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+}
+
+#define UP(dst, vec)                                                                                 \
+    do {                                                                                             \
+        cudaError_t _e;                                                                              \
+        dst = upload(env, vec, &_e);                                                                 \
+        if (_e != cudaSuccess) return fail(env, PPN_E_CUDA, std::string("upload " #vec ": ") + cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" const char* ppn_build_info(void) {
+    return "pypownet_b200 step path; sm_100a; fused warp/CTA-per-env fast-decoupled XB + DC load-flow; built " __DATE__;
+}
+
+extern "C" const char* ppn_last_error(const ppn_env* env) { return env ? env->err.c_str() : g_err.c_str(); }
+
+extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, int device, ppn_env** out) {
+    ppn_env* env = nullptr;
+    if (!g || !cfg || !out || n_envs <= 0) return fail(nullptr, PPN_E_INVALID, "ppn_create: null argument or n_envs <= 0");
+    const int S = g->n_sub, G = g->n_gen, L = g->n_load, N = g->n_line;
+    if (S <= 0 || G <= 0 || L < 0 || N <= 0 || 2 * S > 32000) return fail(nullptr, PPN_E_INVALID, "ppn_create: bad grid sizes");
+    if (!(g->base_mva > 0)) return fail(nullptr, PPN_E_INVALID, "ppn_create: base_mva must be positive");
+    for (int i = 0; i < G; i++) {
+        if (g->gen_sub[i] < 0 || g->gen_sub[i] >= S || (i && g->gen_sub[i] <= g->gen_sub[i - 1]))
+            return fail(nullptr, PPN_E_INVALID, "ppn_create: gen_sub must be strictly ascending substation indices");
+    }
+    for (int i = 0; i < L; i++) {
+        if (g->load_sub[i] < 0 || g->load_sub[i] >= S || (i && g->load_sub[i] <= g->load_sub[i - 1]))
+            return fail(nullptr, PPN_E_INVALID, "ppn_create: load_sub must be strictly ascending substation indices");
+    }
+    for (int i = 0; i < N; i++) {
+        if (g->line_or_sub[i] < 0 || g->line_or_sub[i] >= S || g->line_ex_sub[i] < 0 || g->line_ex_sub[i] >= S)
+            return fail(nullptr, PPN_E_INVALID, "ppn_create: line end out of range");
+        if (g->line_x[i] == 0.0) return fail(nullptr, PPN_E_INVALID, "ppn_create: line with zero reactance");
+    }
+    if (g->slack_sub < 0 || g->slack_sub >= S) return fail(nullptr, PPN_E_INVALID, "ppn_create: slack_sub out of range");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, PPN_E_CUDA, "ppn_create: cudaSetDevice failed (no such CUDA device)");
+    env = new ppn_env();
+    env->device = device;
+    env->B = n_envs;
+    env->S = S; env->G = G; env->L = L; env->N = N; env->NB = 2 * S;
+    env->A = G + L + 3 * N;
+    env->OBSD = 7 * L + 7 * G + 13 * N + S + 6;
+    env->OBS = 9 * L + 9 * G + 18 * N + 2 * S + 6;
+    const int NB = 2 * S;
+
+    // ---- derived static tables
+    std::vector<int> gen_sub(g->gen_sub, g->gen_sub + G), load_sub(g->load_sub, g->load_sub + L),
+        lor(g->line_or_sub, g->line_or_sub + N), lex(g->line_ex_sub, g->line_ex_sub + N);
+    std::vector<int> gen_of_sub(S, -1), load_of_sub(S, -1), adj_ptr(S + 1, 0), adj(2 * N), elem_sub;
+    for (int i = 0; i < G; i++) gen_of_sub[gen_sub[i]] = i;
+    for (int i = 0; i < L; i++) load_of_sub[load_sub[i]] = i;
+    for (int l = 0; l < N; l++) { adj_ptr[lor[l] + 1]++; adj_ptr[lex[l] + 1]++; }
+    for (int s = 0; s < S; s++) adj_ptr[s + 1] += adj_ptr[s];
+    {
+        std::vector<int> fill(adj_ptr.begin(), adj_ptr.end() - 1);
+        for (int l = 0; l < N; l++) { adj[fill[lor[l]]++] = 2 * l; adj[fill[lex[l]]++] = 2 * l + 1; }
+    }
+    elem_sub.insert(elem_sub.end(), gen_sub.begin(), gen_sub.end());
+    elem_sub.insert(elem_sub.end(), load_sub.begin(), load_sub.end());
+    elem_sub.insert(elem_sub.end(), lor.begin(), lor.end());
+    elem_sub.insert(elem_sub.end(), lex.begin(), lex.end());
+    // makeYbus per line: Ys = 1/(r+jx); Ytt = Ys + jb/2; Yff = Ytt/tap^2; Yft = Ytf = -Ys/tap
+    std::vector<double> line_y(8 * N), bp(N), bdc(N);
+    for (int l = 0; l < N; l++) {
+        const double tap = (g->line_tap && g->line_tap[l] != 0.0) ? g->line_tap[l] : 1.0;
+        const std::complex<double> ys = 1.0 / std::complex<double>(g->line_r[l], g->line_x[l]);
+        const std::complex<double> ytt = ys + std::complex<double>(0.0, g->line_b[l] / 2);
+        const std::complex<double> yff = ytt / (tap * tap);
+        const std::complex<double> yft = -ys / tap, ytf = -ys / tap;
+        line_y[8 * l + 0] = yff.real(); line_y[8 * l + 1] = yff.imag();
+        line_y[8 * l + 2] = yft.real(); line_y[8 * l + 3] = yft.imag();
+        line_y[8 * l + 4] = ytf.real(); line_y[8 * l + 5] = ytf.imag();
+        line_y[8 * l + 6] = ytt.real(); line_y[8 * l + 7] = ytt.imag();
+        bp[l] = 1.0 / g->line_x[l];
+        bdc[l] = 1.0 / g->line_x[l] / tap;
+    }
+    std::vector<double> ysh_r(NB), ysh_i(NB), basekv(g->bus_basekv, g->bus_basekv + NB), vm0(g->bus_vm0, g->bus_vm0 + NB),
+        va0(g->bus_va0, g->bus_va0 + NB);
+    for (int b = 0; b < NB; b++) { ysh_r[b] = g->bus_gs[b] / g->base_mva; ysh_i[b] = g->bus_bs[b] / g->base_mva; }
+    std::vector<double> qmin(g->gen_qmin, g->gen_qmin + G), qmax(g->gen_qmax, g->gen_qmax + G),
+        pg0(g->gen_pg0, g->gen_pg0 + G), qg0(g->gen_qg0, g->gen_qg0 + G), vg0(g->gen_vg0, g->gen_vg0 + G),
+        pd0(g->load_pd0, g->load_pd0 + L), qd0(g->load_qd0, g->load_qd0 + L), thermal(g->thermal_limits, g->thermal_limits + N);
+    std::vector<uint8_t> status0(g->line_status0, g->line_status0 + N);
+
+    PpnDevCase& c = env->dc;
+    c.S = S; c.G = G; c.L = L; c.N = N; c.NB = NB; c.A = env->A; c.OBSD = env->OBSD;
+    c.slack_bus = g->slack_sub;
+    c.base_mva = g->base_mva;
+    int* ip; double* dp; uint8_t* up8;
+    UP(ip, gen_sub); c.gen_sub = ip; UP(ip, load_sub); c.load_sub = ip; UP(ip, lor); c.lor_sub = ip; UP(ip, lex); c.lex_sub = ip;
+    UP(ip, gen_of_sub); c.gen_of_sub = ip; UP(ip, load_of_sub); c.load_of_sub = ip;
+    UP(ip, adj_ptr); c.adj_ptr = ip; UP(ip, adj); c.adj = ip; UP(ip, elem_sub); c.elem_sub = ip;
+    UP(dp, line_y); c.line_y = dp; UP(dp, bp); c.line_bp = dp; UP(dp, bdc); c.line_bdc = dp;
+    UP(dp, ysh_r); c.bus_ysh_r = dp; UP(dp, ysh_i); c.bus_ysh_i = dp; UP(dp, basekv); c.bus_basekv = dp;
+    UP(dp, vm0); c.bus_vm0 = dp; UP(dp, va0); c.bus_va0 = dp;
+    UP(dp, qmin); c.gen_qmin = dp; UP(dp, qmax); c.gen_qmax = dp; UP(dp, pg0); c.gen_pg0 = dp; UP(dp, qg0); c.gen_qg0 = dp;
+    UP(dp, vg0); c.gen_vg0 = dp; UP(dp, pd0); c.load_pd0 = dp; UP(dp, qd0); c.load_qd0 = dp; UP(dp, thermal); c.thermal = dp;
+    UP(up8, status0); c.line_status0 = up8;
+
+    // static tail of Observation.as_array (environment.py:583-595)
+    {
+        std::vector<double>& t = env->obs_static;
+        for (int s = 0; s < S; s++) t.push_back((double)g->sub_ids[s]);
+        for (int i = 0; i < L; i++) t.push_back((double)g->sub_ids[load_sub[i]]);
+        for (int i = 0; i < G; i++) t.push_back((double)g->sub_ids[gen_sub[i]]);
+        for (int i = 0; i < N; i++) t.push_back((double)g->sub_ids[lor[i]]);
+        for (int i = 0; i < N; i++) t.push_back((double)g->sub_ids[lex[i]]);
+        for (int i = 0; i < N; i++) t.push_back(thermal[i]);
+        for (int i = 0; i < G + L + 2 * N; i++) t.push_back(0.0);
+    }
+
+    // ---- configuration
+    PpnDevCfg& k = env->dcfg;
+    k.dc = cfg->dc;
+    k.hard_coef = cfg->hard_overflow_coefficient;
+    k.n_hard_broken = cfg->n_timesteps_hard_overflow_is_broken;
+    k.n_soft_consec = cfg->n_timesteps_consecutive_soft_overflow_breaks;
+    k.n_soft_broken = cfg->n_timesteps_soft_overflow_is_broken;
+    k.max_prods_go = cfg->max_number_prods_game_over;
+    k.max_loads_go = cfg->max_number_loads_game_over;
+    k.n_line_react = cfg->n_timesteps_actionned_line_reactionable;
+    k.n_node_react = cfg->n_timesteps_actionned_node_reactionable;
+    k.max_sub = cfg->max_number_actionned_substations;
+    k.max_lines = cfg->max_number_actionned_lines;
+    k.max_total = cfg->max_number_actionned_total;
+    k.hard_mode = cfg->hard_game_over;
+    k.loop_mode = cfg->loop_mode;
+    k.tol = cfg->pf_tol > 0 ? cfg->pf_tol : 1e-6;
+    k.max_it = cfg->pf_max_it > 0 ? cfg->pf_max_it : 25;
+    k.reward_k = cfg->reward_constant;
+    k.seed = cfg->seed;
+    k.max_reset_attempts = 64;
+
+    // ---- threads per env and shared-memory plan
+    int tpe = cfg->threads_per_env;
+    if (tpe == 0) tpe = (NB <= 64) ? 32 : 256;
+    if (tpe != 32 && tpe != 128 && tpe != 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env must be 0, 32, 128 or 256"); }
+    if (tpe == 32 && NB > 64) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "one warp per env supports at most 32 substations"); }
+    env->tpe = tpe;
+    const int fixed = ppn_env_smem_fixed_bytes(S, G, L, N, tpe);
+    int max_smem = 0;
+    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    // un-split solver sizes: B' over (#active - 1) buses, B'' over the PQ buses; room for a few split substations
+    const int n1 = S + 3, n2 = S + 3 - (G > 4 ? 4 : G);
+    int want = n1 * (n1 | 1) + n2 * (n2 | 1);
+    const int worst = 2 * (NB - 1) * ((NB - 1) | 1);
+    if (want > worst) want = worst;
+    env->envs_per_block = tpe == 32 ? 4 : 1;
+    int cap_bytes = max_smem / env->envs_per_block - fixed - 64;
+    if (cap_bytes < 0) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "grid too large for the shared-memory plan"); }
+    int cap = cap_bytes / 8;
+    if (tpe == 32) { if (cap > want) cap = want; }          // small grids: keep occupancy, spill rare big splits to HBM
+    else if (cap > worst) cap = worst;                       // one env per CTA: take what the SM has
+    cap &= ~1;
+    env->mat_cap = cap;
+    env->env_smem_bytes = fixed + cap * 8;
+    env->ws_stride = worst;
+    env->ws_rows = n_envs;
+    env->horizon = cfg->n_timesteps_horizon_maintenance > 0 ? cfg->n_timesteps_horizon_maintenance : 1;
+    CK(cudaMalloc(&env->ws, (size_t)n_envs * worst * sizeof(double)));
+    env->allocs.push_back(env->ws);
+
+    // ---- per-env state
+    env->st.rw = 2 * NB + 2 * L + 3 * G;
+    env->st.tw = (2 * G + L + 3 * N + 15) & ~15;
+    env->st.cw = (3 * N + S + 4 + 3) & ~3;
+    CK(cudaMalloc(&env->st.real, (size_t)n_envs * env->st.rw * sizeof(double)));
+    env->allocs.push_back(env->st.real);
+    CK(cudaMalloc(&env->st.topo, (size_t)n_envs * env->st.tw));
+    env->allocs.push_back(env->st.topo);
+    CK(cudaMalloc(&env->st.cnt, (size_t)n_envs * env->st.cw * sizeof(int32_t)));
+    env->allocs.push_back(env->st.cnt);
+    CK(cudaMemset(env->st.real, 0, (size_t)n_envs * env->st.rw * sizeof(double)));
+    CK(cudaMemset(env->st.topo, 0, (size_t)n_envs * env->st.tw));
+    CK(cudaMemset(env->st.cnt, 0, (size_t)n_envs * env->st.cw * sizeof(int32_t)));
+    CK(cudaMalloc(&env->stats, 8 * sizeof(unsigned long long)));
+    env->allocs.push_back(env->stats);
+    CK(cudaMemset(env->stats, 0, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&env->d_init, (size_t)2 * n_envs * sizeof(int32_t)));
+    env->allocs.push_back(env->d_init);
+    CK(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
+    *out = env;
+    return PPN_OK;
+}
+
+extern "C" void ppn_destroy(ppn_env* env) {
+    if (!env) return;
+    cudaSetDevice(env->device);
+    for (void* p : env->allocs) cudaFree(p);
+    void* pinned[] = {env->h_act, env->h_obs, env->h_reward, env->h_done, env->h_flag, env->h_ill};
+    for (void* p : pinned) if (p) cudaFreeHost(p);
+    void* dev[] = {env->d_act, env->d_obs, env->d_reward, env->d_done, env->d_flag, env->d_ill};
+    for (void* p : dev) if (p) cudaFree(p);
+    if (env->own_stream) cudaStreamDestroy(env->own_stream);
+    delete env;
+}
+
+extern "C" int ppn_load_chronics(ppn_env* env, int n_chronics, const ppn_chronic* t) {
+    if (!env || !t || n_chronics <= 0) return fail(env, PPN_E_INVALID, "ppn_load_chronics: bad arguments");
+    if (env->chronics_loaded) return fail(env, PPN_E_STATE, "ppn_load_chronics: chronics already loaded for this handle");
+    CK(cudaSetDevice(env->device));
+    const int G = env->G, L = env->L, N = env->N;
+    PpnDevChronics& d = env->dch;
+    int o = 0;
+    d.o_pp = o; o += G; d.o_pv = o; o += G; d.o_lp = o; o += L; d.o_lq = o; o += L; d.o_mt = o; o += N; d.o_hz = o; o += N;
+    d.o_ppp = o; o += G; d.o_pvp = o; o += G; d.o_lpp = o; o += L; d.o_lqp = o; o += L; d.o_pm = o; o += N; d.o_dt = o; o += 6;
+    d.row_words = (o + 3) & ~3;
+    d.n_chronics = n_chronics;
+    std::vector<int> row_off(n_chronics), n_rows(n_chronics), ras(n_chronics), liz(n_chronics);
+    long long total = 0;
+    for (int c = 0; c < n_chronics; c++) {
+        if (t[c].n_rows <= 0) return fail(env, PPN_E_INVALID, "ppn_load_chronics: chronic without rows");
+        row_off[c] = (int)total; n_rows[c] = t[c].n_rows; total += t[c].n_rows;
+    }
+    if (total * d.row_words > 0x7fffffffLL * 2) return fail(env, PPN_E_UNSUPPORTED, "ppn_load_chronics: chronic table too large");
+    std::vector<float> rows((size_t)total * d.row_words, 0.f);
+    const int horizon = env->horizon;
+    for (int c = 0; c < n_chronics; c++) {
+        const ppn_chronic& s = t[c];
+        const int T = s.n_rows;
+        ras[c] = -1;
+        for (int r = 0; r < T; r++)
+            if (s.ids[r] == 0) { ras[c] = r + 1 < T ? r + 1 : T - 1; break; }
+        liz[c] = s.ids[T - 1] == 0;
+        for (int r = 0; r < T; r++) {
+            float* w = rows.data() + (size_t)(row_off[c] + r) * d.row_words;
+            memcpy(w + d.o_pp, s.prods_p + (size_t)r * G, G * sizeof(float));
+            memcpy(w + d.o_pv, s.prods_v + (size_t)r * G, G * sizeof(float));
+            memcpy(w + d.o_lp, s.loads_p + (size_t)r * L, L * sizeof(float));
+            memcpy(w + d.o_lq, s.loads_q + (size_t)r * L, L * sizeof(float));
+            memcpy(w + d.o_mt, s.maintenance + (size_t)r * N, N * sizeof(float));
+            memcpy(w + d.o_hz, s.hazards + (size_t)r * N, N * sizeof(float));
+            memcpy(w + d.o_ppp, s.prods_p_planned + (size_t)r * G, G * sizeof(float));
+            memcpy(w + d.o_pvp, s.prods_v_planned + (size_t)r * G, G * sizeof(float));
+            memcpy(w + d.o_lpp, s.loads_p_planned + (size_t)r * L, L * sizeof(float));
+            memcpy(w + d.o_lqp, s.loads_q_planned + (size_t)r * L, L * sizeof(float));
+            // timesteps before planned maintenance (chronic.py:239-246): first row index within the horizon
+            int32_t* pm = reinterpret_cast<int32_t*>(w + d.o_pm);
+            for (int l = 0; l < N; l++) {
+                int first = 0;
+                for (int h = 0; h < horizon && r + h < T; h++)
+                    if (s.maintenance[(size_t)(r + h) * N + l] != 0.f) { first = h; break; }
+                pm[l] = first;
+            }
+            int32_t* dt = reinterpret_cast<int32_t*>(w + d.o_dt);
+            for (int q = 0; q < 6; q++) dt[q] = s.datetimes ? s.datetimes[(size_t)r * 6 + q] : 0;
+        }
+    }
+    float* fp; int* ip;
+    UP(fp, rows); d.rows = fp;
+    UP(ip, row_off); d.row_off = ip; UP(ip, n_rows); d.n_rows = ip; UP(ip, ras); d.row_after_switch = ip; UP(ip, liz); d.last_id_zero = ip;
+    env->chronic_rows = n_rows;
+    env->chronics_loaded = true;
+    return PPN_OK;
+}
+
+static int launch(ppn_env* env, PpnStepArgs& a, cudaStream_t s) {
+    a.ws = env->ws; a.ws_stride = env->ws_stride; a.mat_cap = env->mat_cap; a.stats = env->stats;
+    a.n_envs = env->B;
+    if (a.n_cand <= 0) a.n_cand = 1;
+    if (a.mode == PPN_MODE_SIMULATE && a.n_cand > 1) {
+        // every candidate needs its own spill slice
+        if ((long long)env->B * a.n_cand > env->ws_rows) {
+            double* nws = nullptr;
+            cudaError_t e2 = cudaMalloc(&nws, (size_t)env->B * a.n_cand * env->ws_stride * sizeof(double));
+            if (e2 != cudaSuccess) return fail(env, PPN_E_CUDA, std::string("workspace for simulate: ") + cudaGetErrorString(e2));
+            env->allocs.push_back(nws);
+            env->ws = nws; env->ws_rows = (long long)env->B * a.n_cand;
+            a.ws = nws;
+        }
+    }
+    int rc = ppn_launch_step(&env->dc, &env->dch, &env->dcfg, &env->st, &a, env->tpe, env->envs_per_block, env->env_smem_bytes, s);
+    env->launches++;
+    if (rc != 0) return fail(env, PPN_E_CUDA, std::string("step kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+    return PPN_OK;
+}
+
+extern "C" int ppn_reset(ppn_env* env, const int32_t* chronic_idx_host, const int32_t* row0_host, double* obs_dev,
+                         int64_t obs_stride, int32_t* flag_dev, void* stream) {
+    if (!env) return fail(nullptr, PPN_E_INVALID, "ppn_reset: null handle");
+    if (!env->chronics_loaded) return fail(env, PPN_E_STATE, "ppn_reset: load chronics first");
+    if (obs_dev && obs_stride < env->OBSD) return fail(env, PPN_E_INVALID, "ppn_reset: obs_stride smaller than the dynamic observation");
+    CK(cudaSetDevice(env->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = env->B;
+    std::vector<int32_t> init(2 * (size_t)B, 0);
+    for (int e = 0; e < B; e++) {
+        const int c = chronic_idx_host ? chronic_idx_host[e] : 0;
+        if (c < 0 || c >= env->dch.n_chronics) return fail(env, PPN_E_INVALID, "ppn_reset: chronic index out of range");
+        const int r = row0_host ? row0_host[e] : 0;
+        if (r < 0 || r >= env->chronic_rows[c]) return fail(env, PPN_E_INVALID, "ppn_reset: first row out of range");
+        init[e] = c; init[B + e] = r;
+    }
+    CK(cudaMemcpyAsync(env->d_init, init.data(), init.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));   // `init` is pageable and dies with this frame
+    PpnStepArgs a{};
+    a.mode = PPN_MODE_INIT;
+    a.init_chronic = env->d_init; a.init_row0 = env->d_init + B;
+    a.obs = obs_dev; a.obs_stride = obs_stride; a.flag = flag_dev;
+    int rc = launch(env, a, s);
+    if (rc == PPN_OK) env->initialised = true;
+    return rc;
+}
+
+static int check_ready(ppn_env* env, const char* who) {
+    if (!env) return fail(nullptr, PPN_E_INVALID, std::string(who) + ": null handle");
+    if (!env->initialised) return fail(env, PPN_E_STATE, std::string(who) + ": call ppn_load_chronics and ppn_reset first");
+    return PPN_OK;
+}
+
+extern "C" int ppn_step(ppn_env* env, const uint8_t* act_dev, double* obs_dev, int64_t obs_stride, double* reward_dev,
+                        uint8_t* done_dev, int32_t* flag_dev, uint8_t* illegal_dev, int auto_reset, void* stream) {
+    int rc = check_ready(env, "ppn_step");
+    if (rc) return rc;
+    if (obs_dev && obs_stride < env->OBSD) return fail(env, PPN_E_INVALID, "ppn_step: obs_stride smaller than the dynamic observation");
+    CK(cudaSetDevice(env->device));
+    PpnStepArgs a{};
+    a.mode = PPN_MODE_STEP; a.auto_reset = auto_reset; a.act = act_dev;
+    a.obs = obs_dev; a.obs_stride = obs_stride; a.reward = reward_dev; a.done = done_dev; a.flag = flag_dev; a.illegal = illegal_dev;
+    return launch(env, a, (cudaStream_t)stream);
+}
+
+extern "C" int ppn_simulate(ppn_env* env, int n_candidates, const uint8_t* act_dev, double* obs_dev, int64_t obs_stride,
+                            double* reward_dev, uint8_t* done_dev, int32_t* flag_dev, uint8_t* illegal_dev, void* stream) {
+    int rc = check_ready(env, "ppn_simulate");
+    if (rc) return rc;
+    if (n_candidates <= 0) return fail(env, PPN_E_INVALID, "ppn_simulate: n_candidates must be positive");
+    if (obs_dev && obs_stride < env->OBSD) return fail(env, PPN_E_INVALID, "ppn_simulate: obs_stride smaller than the dynamic observation");
+    CK(cudaSetDevice(env->device));
+    PpnStepArgs a{};
+    a.mode = PPN_MODE_SIMULATE; a.n_cand = n_candidates; a.act = act_dev;
+    a.obs = obs_dev; a.obs_stride = obs_stride; a.reward = reward_dev; a.done = done_dev; a.flag = flag_dev; a.illegal = illegal_dev;
+    return launch(env, a, (cudaStream_t)stream);
+}
+
+extern "C" int ppn_process_game_over(ppn_env* env, const uint8_t* mask_dev, double* obs_dev, int64_t obs_stride, void* stream) {
+    int rc = check_ready(env, "ppn_process_game_over");
+    if (rc) return rc;
+    if (obs_dev && obs_stride < env->OBSD) return fail(env, PPN_E_INVALID, "ppn_process_game_over: obs_stride smaller than the dynamic observation");
+    CK(cudaSetDevice(env->device));
+    PpnStepArgs a{};
+    a.mode = PPN_MODE_GAME_OVER; a.mask = mask_dev; a.obs = obs_dev; a.obs_stride = obs_stride;
+    return launch(env, a, (cudaStream_t)stream);
+}
+
+// Game.is_action_valid (game.py:755-760): the legality tests of _verify_illegal_action, no state change.
+__global__ void ppn_action_valid_kernel(PpnDevCase c, PpnDevCfg cfg, PpnDevState st, const uint8_t* act, uint8_t* valid, int B) {
+    const int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (env >= B) return;
+    const int lane = threadIdx.x & 31;
+    const int NT = c.G + c.L + 2 * c.N;
+    const uint8_t* a = act + (size_t)env * c.A;
+    const int32_t* cnt = st.cnt + (size_t)env * st.cw;
+    int ns = 0, nl = 0, bad = 0;
+    for (int s = lane; s < c.S; s += 32) {
+        bool ch = false;
+        for (int i = 0; i < NT; i++) ch |= (a[i] != 0 && c.elem_sub[i] == s);
+        ns += ch;
+        bad += ch && cnt[3 * c.N + s] > 0;
+    }
+    for (int l = lane; l < c.N; l += 32) {
+        const bool sw = a[NT + l] == 1;
+        nl += sw;
+        bad += sw && (cnt[l] > 0 || cnt[c.N + l] > 0);
+    }
+    ns = __reduce_add_sync(0xffffffffu, ns); nl = __reduce_add_sync(0xffffffffu, nl); bad = __reduce_add_sync(0xffffffffu, bad);
+    if (lane == 0) valid[env] = !(ns > cfg.max_sub || nl > cfg.max_lines || ns + nl > cfg.max_total || bad > 0);
+}
+
+extern "C" int ppn_action_valid(ppn_env* env, const uint8_t* act_dev, uint8_t* valid_dev, void* stream) {
+    int rc = check_ready(env, "ppn_action_valid");
+    if (rc) return rc;
+    if (!act_dev || !valid_dev) return fail(env, PPN_E_INVALID, "ppn_action_valid: null buffer");
+    CK(cudaSetDevice(env->device));
+    ppn_action_valid_kernel<<<(env->B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(env->dc, env->dcfg, env->st, act_dev, valid_dev, env->B);
+    env->launches++;
+    CK(cudaGetLastError());
+    return PPN_OK;
+}
+
+static int ensure_staging(ppn_env* env) {
+    if (env->h_act) return PPN_OK;
+    const size_t B = env->B;
+    CK(cudaMallocHost(&env->h_act, B * env->A));
+    CK(cudaMalloc(&env->d_act, B * env->A));
+    CK(cudaMallocHost(&env->h_obs, B * env->OBSD * sizeof(double)));
+    CK(cudaMalloc(&env->d_obs, B * env->OBSD * sizeof(double)));
+    CK(cudaMallocHost(&env->h_reward, B * 5 * sizeof(double)));
+    CK(cudaMalloc(&env->d_reward, B * 5 * sizeof(double)));
+    CK(cudaMallocHost(&env->h_done, B));
+    CK(cudaMalloc(&env->d_done, B));
+    CK(cudaMallocHost(&env->h_flag, B * sizeof(int32_t)));
+    CK(cudaMalloc(&env->d_flag, B * sizeof(int32_t)));
+    const size_t iw = 1 + 2 * env->N + env->S;
+    CK(cudaMallocHost(&env->h_ill, B * iw));
+    CK(cudaMalloc(&env->d_ill, B * iw));
+    return PPN_OK;
+}
+
+extern "C" int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_host, int64_t obs_stride, double* reward_host,
+                             uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset) {
+    int rc = check_ready(env, "ppn_step_host");
+    if (rc) return rc;
+    if (obs_host && obs_stride < env->OBSD) return fail(env, PPN_E_INVALID, "ppn_step_host: obs_stride smaller than the dynamic observation");
+    CK(cudaSetDevice(env->device));
+    rc = ensure_staging(env);
+    if (rc) return rc;
+    cudaStream_t s = env->own_stream;
+    const size_t B = env->B, iw = 1 + 2 * env->N + env->S;
+    if (act_host) {
+        memcpy(env->h_act, act_host, B * env->A);
+        CK(cudaMemcpyAsync(env->d_act, env->h_act, B * env->A, cudaMemcpyHostToDevice, s));
+    }
+    PpnStepArgs a{};
+    a.mode = PPN_MODE_STEP; a.auto_reset = auto_reset; a.act = act_host ? env->d_act : nullptr;
+    a.obs = obs_host ? env->d_obs : nullptr; a.obs_stride = env->OBSD;
+    a.reward = env->d_reward; a.done = env->d_done; a.flag = env->d_flag; a.illegal = illegal_host ? env->d_ill : nullptr;
+    rc = launch(env, a, s);
+    if (rc) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(env->h_obs, env->d_obs, B * env->OBSD * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(env->h_reward, env->d_reward, B * 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(env->h_done, env->d_done, B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(env->h_flag, env->d_flag, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (illegal_host) CK(cudaMemcpyAsync(env->h_ill, env->d_ill, B * iw, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (obs_host) {
+        // rows of envs that ended (and were not auto-reset) hold no observation: leave the caller's row untouched
+        for (size_t e = 0; e < B; e++)
+            if (auto_reset || !env->h_done[e])
+                memcpy(obs_host + e * obs_stride, env->h_obs + e * env->OBSD, env->OBSD * sizeof(double));
+    }
+    if (reward_host) memcpy(reward_host, env->h_reward, B * 5 * sizeof(double));
+    if (done_host) memcpy(done_host, env->h_done, B);
+    if (flag_host) memcpy(flag_host, env->h_flag, B * sizeof(int32_t));
+    if (illegal_host) memcpy(illegal_host, env->h_ill, B * iw);
+    return PPN_OK;
+}
+
+extern "C" int ppn_state_width(const ppn_env* env, int field) {
+    if (!env) return PPN_E_INVALID;
+    switch (field) {
+        case PPN_STATE_REAL: return env->st.rw;
+        case PPN_STATE_TOPOLOGY: return 2 * env->G + env->L + 3 * env->N;
+        case PPN_STATE_COUNTERS: return 3 * env->N + env->S + 4;
+        default: return PPN_E_INVALID;
+    }
+}
+
+static int copy_state(ppn_env* env, int field, void* user, bool to_user, cudaStream_t s) {
+    if (!env || !user) return fail(env, PPN_E_INVALID, "ppn_get/set_state: null argument");
+    CK(cudaSetDevice(env->device));
+    const int w = ppn_state_width(env, field);
+    if (w < 0) return fail(env, PPN_E_INVALID, "ppn_get/set_state: unknown field");
+    size_t esz, stride; char* base;
+    if (field == PPN_STATE_REAL) { esz = 8; stride = env->st.rw; base = (char*)env->st.real; }
+    else if (field == PPN_STATE_TOPOLOGY) { esz = 1; stride = env->st.tw; base = (char*)env->st.topo; }
+    else { esz = 4; stride = env->st.cw; base = (char*)env->st.cnt; }
+    if (to_user) CK(cudaMemcpy2DAsync(user, w * esz, base, stride * esz, w * esz, env->B, cudaMemcpyDeviceToDevice, s));
+    else CK(cudaMemcpy2DAsync(base, stride * esz, user, w * esz, w * esz, env->B, cudaMemcpyDeviceToDevice, s));
+    return PPN_OK;
+}
+
+extern "C" int ppn_get_state(ppn_env* env, int field, void* out_dev, void* stream) {
+    return copy_state(env, field, out_dev, true, (cudaStream_t)stream);
+}
+extern "C" int ppn_set_state(ppn_env* env, int field, const void* in_dev, void* stream) {
+    return copy_state(env, field, const_cast<void*>(in_dev), false, (cudaStream_t)stream);
+}
+
+extern "C" int ppn_observation_static(ppn_env* env, double* out_host) {
+    if (!env || !out_host) return fail(env, PPN_E_INVALID, "ppn_observation_static: null argument");
+    memcpy(out_host, env->obs_static.data(), env->obs_static.size() * sizeof(double));
+    return PPN_OK;
+}
+
+extern "C" int ppn_n_envs(const ppn_env* env) { return env ? env->B : PPN_E_INVALID; }
+extern "C" int ppn_action_length(const ppn_env* env) { return env ? env->A : PPN_E_INVALID; }
+extern "C" int ppn_obs_length(const ppn_env* env) { return env ? env->OBS : PPN_E_INVALID; }
+extern "C" int ppn_obs_dynamic_length(const ppn_env* env) { return env ? env->OBSD : PPN_E_INVALID; }
+extern "C" int ppn_device(const ppn_env* env) { return env ? env->device : PPN_E_INVALID; }
+
+extern "C" int ppn_get_counters(ppn_env* env, int64_t* out_host) {
+    if (!env || !out_host) return fail(env, PPN_E_INVALID, "ppn_get_counters: null argument");
+    CK(cudaSetDevice(env->device));
+    unsigned long long h[8];
+    CK(cudaMemcpy(h, env->stats, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; i++) out_host[i] = (int64_t)h[i];
+    out_host[5] = env->launches;
+    out_host[6] = env->env_smem_bytes;
+    out_host[7] = env->tpe;
+    return PPN_OK;
+}

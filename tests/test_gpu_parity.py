@@ -1,0 +1,127 @@
+"""GPU parity: the CUDA step path (through the C ABI) against (1) the fixtures recorded from the unmodified
+reference and (2) the CPU oracle on batches of envs started at different chronics / rows.
+Tolerance: 1e-6 on every observation entry (BASELINE.json north_star: bus voltage magnitudes/angles to 1e-6), the
+suite asserts the tighter 1e-7 seen in practice; line status, done and flag codes bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Fixture, fixture_names
+from oracle.flat import FlatEnv, Config
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-7
+
+
+def vec_env(fx, B, **kw):
+    from pypownet_b200.vec_env import VecRunEnv
+    return VecRunEnv(fx.case, fx.config, fx.chronics, B, device=0, game_over_mode=fx.mode,
+                     reward_constant=fx.reward_constant, thermal_limits=fx.thermal_limits, **kw)
+
+
+@pytest.mark.parametrize('name', fixture_names())
+def test_cuda_reproduces_reference_fixture(name):
+    fx = Fixture(name)
+    B = 3
+    env = vec_env(fx, B)
+    nd = fx.case.obs_dynamic_length
+    obs0 = env.obs.cpu().numpy()
+    assert np.max(np.abs(obs0[0] - fx.obs0)) < TOL
+    worst = 0.0
+    for t in range(len(fx.actions)):
+        if fx.has_sim:
+            so, sr, sd, sf = env.simulate(np.repeat(fx.sim_actions[t][None], B, axis=0))
+            assert bool(sd[1].item()) == bool(fx.sim_done[t]) and int(sf[1].item()) == int(fx.sim_flag[t]), t
+            if not fx.sim_done[t]:
+                worst = max(worst, float(np.max(np.abs(so[1].cpu().numpy() - fx.sim_obs[t]))))
+            if fx.default_reward:
+                assert np.max(np.abs(sr[1].cpu().numpy() - fx.sim_reward[t])) < TOL
+        obs, reward, done, flag = env.step(np.repeat(fx.actions[t][None], B, axis=0))
+        d, f = done.cpu().numpy(), flag.cpu().numpy()
+        assert np.all(d == int(fx.done[t])) and np.all(f == int(fx.flag[t])), 'step %d: %s %s' % (t, d, f)
+        if fx.default_reward:
+            assert np.max(np.abs(reward.cpu().numpy() - fx.reward[t][None])) < TOL, t
+        if fx.done[t]:
+            obs = env.process_game_over(done)
+            expect = fx.reset_obs[t]
+        else:
+            expect = fx.obs[t]
+        got = obs.cpu().numpy()
+        assert np.array_equal(got[0], got[B - 1])
+        err = float(np.max(np.abs(got[0] - expect)))
+        assert err < TOL, 'step %d: |cuda - reference| = %g at %d' % (t, err, int(np.argmax(np.abs(got[0] - expect))))
+        worst = max(worst, err)
+    assert worst < TOL
+
+
+@pytest.mark.parametrize('name,steps', [('d14_ac_random', 120), ('d30_ac_random', 60), ('d118_ac_random', 25),
+                                        ('d14_dc_random', 60)])
+def test_cuda_matches_oracle_on_a_ragged_batch(name, steps):
+    """Envs start on different chronics and rows and receive different random actions; auto-reset as Runner does."""
+    fx = Fixture(name)
+    B = 24
+    rng = np.random.default_rng(11)
+    nch = len(fx.chronics)
+    start_c = rng.integers(0, nch, size=B).astype(np.int32)
+    start_r = np.array([rng.integers(0, fx.chronics[c].n_rows - 1) for c in start_c], dtype=np.int32)
+    start_r[0] = 0
+    env = vec_env(fx, B, start_chronics=start_c, start_rows=start_r)
+    cfg = Config(fx.config, game_over_mode=fx.mode, reward_constant=fx.reward_constant, n_sub=fx.case.n_sub)
+    refs = [FlatEnv(fx.case, cfg, fx.chronics, start_id=int(start_c[e]), thermal_limits=fx.thermal_limits,
+                    start_row=int(start_r[e])) for e in range(B)]
+    nd = fx.case.obs_dynamic_length
+    got0 = env.obs.cpu().numpy()
+    for e in range(B):
+        assert np.max(np.abs(got0[e, :nd] - refs[e].observation_dynamic())) < TOL, e
+    case = fx.case
+    worst = 0.0
+    for t in range(steps):
+        acts = np.zeros((B, case.action_length), dtype=np.uint8)
+        for e in range(B):
+            if rng.random() < .5:
+                s = rng.integers(case.n_sub)
+                el = np.flatnonzero(case.elem_sub == s)
+                acts[e, el] = rng.integers(0, 2, size=len(el))
+            if rng.random() < .5:
+                acts[e, case.n_gen + case.n_load + 2 * case.n_line + rng.integers(case.n_line)] = 1
+        obs, reward, done, flag = env.step(acts, auto_reset=True)
+        got, r, d, f = obs.cpu().numpy(), reward.cpu().numpy(), done.cpu().numpy(), flag.cpu().numpy()
+        for e in range(B):
+            o2, r2, d2, f2, _ = refs[e].step(acts[e])
+            assert (bool(d[e]), int(f[e])) == (bool(d2), int(f2)), 'step %d env %d' % (t, e)
+            assert np.max(np.abs(r[e] - r2)) < TOL
+            if d2:
+                o2 = refs[e].process_game_over()
+            err = float(np.max(np.abs(got[e, :nd] - o2)))
+            assert err < TOL, 'step %d env %d: %g' % (t, e, err)
+            worst = max(worst, err)
+    c = env.counters()
+    assert c['env_steps'] >= B * steps and c['loadflows'] >= c['env_steps']
+
+
+def test_step_host_matches_device_entry_point():
+    fx = Fixture('d14_ac_nothing')
+    B = 5
+    e1, e2 = vec_env(fx, B), vec_env(fx, B)
+    obs_h = np.zeros((B, fx.case.obs_dynamic_length))
+    for t in range(30):
+        a = np.repeat(fx.actions[t][None], B, axis=0)
+        o1, r1, d1, f1 = e1.step(a, auto_reset=True)
+        _, r2, d2, f2 = e2.step_host(a, obs_out=obs_h, auto_reset=True)
+        assert np.array_equal(o1.cpu().numpy()[:, :obs_h.shape[1]], obs_h)
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy(), d2)
+        assert np.array_equal(f1.cpu().numpy(), f2)
+
+
+def test_is_action_valid_and_illegal_masks():
+    fx = Fixture('d14_ac_random')
+    env = vec_env(fx, 2)
+    case = fx.case
+    a = np.zeros((2, case.action_length), dtype=np.uint8)
+    a[1, :] = 1                                         # far too many switches
+    v = env.is_action_valid(a).cpu().numpy()
+    assert v[0] and not v[1]
+    env.step(a)
+    ill = env.illegal.cpu().numpy()
+    assert ill[1, 0] == 1 and ill[0].sum() == 0
+    assert int(env.flag[1].item()) in (1, 2, 3, 4)
