@@ -205,23 +205,24 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
 
     // ---- threads per env and shared-memory plan
     int tpe = cfg->threads_per_env;
-    if (tpe == 0) tpe = (NB <= 64) ? 32 : 256;
-    if (tpe != 32 && tpe != 128 && tpe != 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env must be 0, 32, 128 or 256"); }
-    if (tpe == 32 && NB > 64) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "one warp per env supports at most 32 substations"); }
+    if (tpe == 0) tpe = (NB <= 32) ? 16 : ((NB <= 64) ? 32 : 256);
+    if (tpe != 16 && tpe != 32 && tpe != 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env must be 0, 16, 32 or 256"); }
+    if ((tpe == 16 && NB > 32) || (tpe == 32 && NB > 64) || NB > 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env too small for this grid (16: <= 16 substations, 32: <= 32, 256: <= 128)"); }
     env->tpe = tpe;
     const int fixed = ppn_env_smem_fixed_bytes(S, G, L, N, tpe);
     int max_smem = 0;
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    // un-split solver sizes: B' over (#active - 1) buses, B'' over the PQ buses; room for a few split substations
-    const int n1 = S + 3, n2 = S + 3 - (G > 4 ? 4 : G);
+    // Shared-memory room for B' and B'': the un-split grid (n1 = S-1 buses) with up to two generators off (n2 = PQ
+    // buses); larger systems (node splitting, more generators off) use the env's slice of the HBM workspace.
+    const int n1 = S - 1, n2 = S - 1 - (G > 3 ? G - 3 : 0);
     int want = n1 * (n1 | 1) + n2 * (n2 | 1);
     const int worst = 2 * (NB - 1) * ((NB - 1) | 1);
     if (want > worst) want = worst;
-    env->envs_per_block = tpe == 32 ? 4 : 1;
+    env->envs_per_block = tpe == 16 ? 2 : 1;                 // one warp per CTA for the sub-warp / warp kernels
     int cap_bytes = max_smem / env->envs_per_block - fixed - 64;
     if (cap_bytes < 0) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "grid too large for the shared-memory plan"); }
     int cap = cap_bytes / 8;
-    if (tpe == 32) { if (cap > want) cap = want; }          // small grids: keep occupancy, spill rare big splits to HBM
+    if (tpe <= 32) { if (cap > want) cap = want; }          // small grids: keep occupancy, spill rare big systems to HBM
     else if (cap > worst) cap = worst;                       // one env per CTA: take what the SM has
     cap &= ~1;
     env->mat_cap = cap;

@@ -1,7 +1,8 @@
-// Batched pypownet step path as one fused sm_100a kernel: every env (grid copy) is owned by TPE threads -- one warp
-// for IEEE-14/30 sized grids, one CTA for IEEE-118 -- that keep the whole working set of the timestep in shared
-// memory: topology, bus types, fast-decoupled B'/B'' inverses, voltages, flows, counters.  HBM traffic per env-step
-// is the state row in, one chronic record in, the action in, and state row + observation + reward/done/flag out.
+// Batched pypownet step path as one fused sm_100a kernel: every env (grid copy) is owned by TPE threads -- half a warp
+// for IEEE-14, one warp for IEEE-30 sized grids, one CTA for IEEE-118 -- that keep the whole working set of the
+// timestep in shared memory: topology, bus types, fast-decoupled B'/B'' inverses, voltages, flows, counters.  HBM
+// traffic per env-step is the state row in, one chronic record in, the action in, and state row + observation +
+// reward/done/flag out.
 //
 // Reference path (pypownet @ /root/reference):
 //   Game.step / apply_action / _verify_illegal_action        pypownet/game.py:591-753, 799-885
@@ -26,140 +27,151 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------- env-wide primitives
-template <int TPE> __device__ __forceinline__ void env_sync() {
-    if (TPE == 32) __syncwarp(); else __syncthreads();
+// An env is owned by a "group": TPE <= 32 lanes of one warp (mask = the group's lanes), or a whole CTA (TPE > 32).
+template <int TPE> __device__ __forceinline__ void env_sync(unsigned mask) {
+    if (TPE <= 32) __syncwarp(mask); else __syncthreads();
 }
 
-template <int TPE> __device__ __forceinline__ bool env_any(bool p) {
-    if (TPE == 32) return __any_sync(PPN_FULL, p);
+template <int TPE> __device__ __forceinline__ bool env_any(bool p, unsigned mask) {
+    if (TPE <= 32) return __any_sync(mask, p);
     return __syncthreads_or(p) != 0;
 }
 
 // NaN-propagating maximum over the env's threads, identical in every thread, fixed order (deterministic).
-template <int TPE> __device__ __forceinline__ double env_max_nan(double v, double* red, int tid) {
+template <int TPE> __device__ __forceinline__ double env_max_nan(double v, double* red, int tid, unsigned mask) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double w = __shfl_xor_sync(PPN_FULL, v, o);
+    for (int o = (TPE < 32 ? TPE : 32) / 2; o > 0; o >>= 1) {
+        double w = __shfl_xor_sync(TPE <= 32 ? mask : PPN_FULL, v, o);
         v = (w > v || w != w) ? w : v;
     }
-    if (TPE == 32) return v;
+    if (TPE <= 32) return v;
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
     double r = red[0];
 #pragma unroll
-    for (int k = 1; k < TPE / 32; k++) {
+    for (int k = 1; k < (TPE + 31) / 32; k++) {
         double w = red[k];
         r = (w > r || w != w) ? w : r;
     }
     return r;
 }
 
-template <int TPE> __device__ __forceinline__ int env_sum_int(int v, int* red, int tid) {
-    v = __reduce_add_sync(PPN_FULL, v);
-    if (TPE == 32) return v;
+template <int TPE> __device__ __forceinline__ int env_sum_int(int v, int* red, int tid, unsigned mask) {
+    v = __reduce_add_sync(TPE <= 32 ? mask : PPN_FULL, v);
+    if (TPE <= 32) return v;
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
     int r = 0;
 #pragma unroll
-    for (int k = 0; k < TPE / 32; k++) r += red[k];
+    for (int k = 0; k < (TPE + 31) / 32; k++) r += red[k];
     return r;
 }
 
-template <int TPE> __device__ __forceinline__ double env_sum_double(double v, double* red, int tid) {
+template <int TPE> __device__ __forceinline__ double env_sum_double(double v, double* red, int tid, unsigned mask) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PPN_FULL, v, o);
-    if (TPE == 32) return v;
+    for (int o = (TPE < 32 ? TPE : 32) / 2; o > 0; o >>= 1) v += __shfl_xor_sync(TPE <= 32 ? mask : PPN_FULL, v, o);
+    if (TPE <= 32) return v;
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
     double r = 0;
 #pragma unroll
-    for (int k = 0; k < TPE / 32; k++) r += red[k];
+    for (int k = 0; k < (TPE + 31) / 32; k++) r += red[k];
     return r;
 }
 
 // ------------------------------------------------------------------------------------------------------ env context
-template <int TPE> struct Env {
-    int tid;
-    int S, G, L, N, NB;
-    // doubles
-    double *vm, *va, *vr, *vi, *pin, *qin, *P, *Q, *sr, *si, *pdb, *qdb;  // [NB]
-    double *pf, *qf, *pt, *qt, *amp;                                        // [N]
-    double *lpd, *lqd;                                                      // [L]
-    double *gpg, *gqg, *gvg, *gkv;                                          // [G]
-    double* redd;
-    double* mat;
-    // ints
-    int *recon, *lreact, *soft, *nreact, *cursor;
-    int* redi;
-    int* misc;  // [8]
-    short *fbus, *tbus, *idxp, *idxq, *busp, *busq, *gbus, *lbus;
-    uint8_t *gnode, *lnode, *onode, *enode, *status, *gstat;  // topo row
-    uint8_t *btype, *mark, *over, *act, *subch, *ill;
+// Grid sizes: compile-time for the three IEEE families (array offsets fold into the instructions, loops unroll),
+// run-time for any other grid.
+template <int S_, int G_, int L_, int N_> struct StaticDims {
+    static constexpr int S = S_, G = G_, L = L_, N = N_, NB = 2 * S_, A = G_ + L_ + 3 * N_;
+    __device__ __forceinline__ void init_dims(const PpnDevCase&) {}
+};
+struct DynDims {
+    int S, G, L, N, NB, A;
+    __device__ __forceinline__ void init_dims(const PpnDevCase& c) { S = c.S; G = c.G; L = c.L; N = c.N; NB = c.NB; A = c.A; }
 };
 
-template <int TPE>
-__device__ __forceinline__ void env_carve(Env<TPE>& e, unsigned char* base, const PpnDevCase& c, int mat_cap) {
-    const int S = c.S, G = c.G, L = c.L, N = c.N, NB = c.NB;
-    e.S = S; e.G = G; e.L = L; e.N = N; e.NB = NB;
-    double* d = reinterpret_cast<double*>(base);
-    e.vm = d; d += NB; e.va = d; d += NB; e.vr = d; d += NB; e.vi = d; d += NB;
-    e.pin = d; d += NB; e.qin = d; d += NB; e.P = d; d += NB; e.Q = d; d += NB;
-    e.sr = d; d += NB; e.si = d; d += NB; e.pdb = d; d += NB; e.qdb = d; d += NB;
-    e.pf = d; d += N; e.qf = d; d += N; e.pt = d; d += N; e.qt = d; d += N; e.amp = d; d += N;
-    e.lpd = d; d += L; e.lqd = d; d += L;
-    e.gpg = d; d += G; e.gqg = d; d += G; e.gvg = d; d += G; e.gkv = d; d += G;
-    e.redd = d; d += (TPE / 32) * 2;
-    e.mat = d; d += mat_cap;
-    int* ip = reinterpret_cast<int*>(d);
-    e.recon = ip; ip += N; e.lreact = ip; ip += N; e.soft = ip; ip += N; e.nreact = ip; ip += S;
-    e.cursor = ip; ip += 4;
-    e.redi = ip; ip += (TPE / 32) * 2;
-    e.misc = ip; ip += 8;
-    short* sp = reinterpret_cast<short*>(ip);
-    e.fbus = sp; sp += N; e.tbus = sp; sp += N;
-    e.idxp = sp; sp += NB; e.idxq = sp; sp += NB; e.busp = sp; sp += NB; e.busq = sp; sp += NB;
-    e.gbus = sp; sp += G; e.lbus = sp; sp += L;
-    uintptr_t up = (reinterpret_cast<uintptr_t>(sp) + 3) & ~uintptr_t(3);
-    uint8_t* bp = reinterpret_cast<uint8_t*>(up);
-    e.gnode = bp; bp += G; e.lnode = bp; bp += L; e.onode = bp; bp += N; e.enode = bp; bp += N;
-    e.status = bp; bp += N; e.gstat = bp; bp += G;
-    e.btype = bp; bp += NB; e.mark = bp; bp += NB; e.over = bp; bp += N;
-    e.act = bp; bp += c.A; e.subch = bp; bp += S; e.ill = bp; bp += 1 + 2 * N + S;
-}
+// Shared-memory image of one env.  Layout (must match ppn_env_smem_fixed_bytes): doubles | int32 | int16 | bytes |
+// pad to 16 | matrix area.  Every array is `base + offset(dims)`; nothing but `base` lives in a register.
+template <int TPE, class D> struct Env : D {
+    int tid;
+    unsigned mask;   // lanes of this env's group (TPE <= 32)
+    int shift;       // first lane of the group
+    unsigned char* base;
+    int fixed_bytes;
+    static constexpr int NW = (TPE + 31) / 32;
+#define PPN_DBL(name, expr) __device__ __forceinline__ double* name() const { return reinterpret_cast<double*>(base) + (expr); }
+    PPN_DBL(vm, 0) PPN_DBL(va, this->NB) PPN_DBL(vr, 2 * this->NB) PPN_DBL(vi, 3 * this->NB)
+    PPN_DBL(pin, 4 * this->NB) PPN_DBL(qin, 5 * this->NB) PPN_DBL(P, 6 * this->NB) PPN_DBL(Q, 7 * this->NB)
+    PPN_DBL(ydr, 8 * this->NB) PPN_DBL(ydi, 9 * this->NB) PPN_DBL(cs, 10 * this->NB) PPN_DBL(sn, 11 * this->NB)
+    PPN_DBL(pf, 12 * this->NB) PPN_DBL(qf, 12 * this->NB + this->N) PPN_DBL(pt, 12 * this->NB + 2 * this->N)
+    PPN_DBL(qt, 12 * this->NB + 3 * this->N) PPN_DBL(amp, 12 * this->NB + 4 * this->N)
+    PPN_DBL(lpd, 12 * this->NB + 5 * this->N) PPN_DBL(lqd, 12 * this->NB + 5 * this->N + this->L)
+    PPN_DBL(gpg, 12 * this->NB + 5 * this->N + 2 * this->L) PPN_DBL(gqg, 12 * this->NB + 5 * this->N + 2 * this->L + this->G)
+    PPN_DBL(gvg, 12 * this->NB + 5 * this->N + 2 * this->L + 2 * this->G)
+    PPN_DBL(gkv, 12 * this->NB + 5 * this->N + 2 * this->L + 3 * this->G)
+    PPN_DBL(redd, 12 * this->NB + 5 * this->N + 2 * this->L + 4 * this->G)
+#undef PPN_DBL
+    __device__ __forceinline__ int n_dbl() const { return 12 * this->NB + 5 * this->N + 2 * this->L + 4 * this->G + 2 * NW; }
+#define PPN_I32(name, expr) __device__ __forceinline__ int* name() const { return reinterpret_cast<int*>(base + 8 * n_dbl()) + (expr); }
+    PPN_I32(recon, 0) PPN_I32(lreact, this->N) PPN_I32(soft, 2 * this->N) PPN_I32(nreact, 3 * this->N)
+    PPN_I32(cursor, 3 * this->N + this->S) PPN_I32(redi, 3 * this->N + this->S + 4) PPN_I32(misc, 3 * this->N + this->S + 4 + 2 * NW)
+#undef PPN_I32
+    __device__ __forceinline__ int n_i32() const { return 3 * this->N + this->S + 4 + 2 * NW + 8; }
+#define PPN_I16(name, expr) __device__ __forceinline__ short* name() const { return reinterpret_cast<short*>(base + 8 * n_dbl() + 4 * n_i32()) + (expr); }
+    PPN_I16(fbus, 0) PPN_I16(tbus, this->N) PPN_I16(idxp, 2 * this->N) PPN_I16(idxq, 2 * this->N + this->NB)
+    PPN_I16(busp, 2 * this->N + 2 * this->NB) PPN_I16(busq, 2 * this->N + 3 * this->NB)
+    PPN_I16(gbus, 2 * this->N + 4 * this->NB) PPN_I16(lbus, 2 * this->N + 4 * this->NB + this->G)
+    PPN_I16(ebus, 2 * this->N + 4 * this->NB + this->G + this->L) PPN_I16(eoth, 4 * this->N + 4 * this->NB + this->G + this->L)
+#undef PPN_I16
+    __device__ __forceinline__ int n_i16() const { return 6 * this->N + 4 * this->NB + this->G + this->L; }
+#define PPN_U8(name, expr) __device__ __forceinline__ uint8_t* name() const { return base + 8 * n_dbl() + 4 * n_i32() + ((2 * n_i16() + 3) & ~3) + (expr); }
+    // topo row: gnode | lnode | onode | enode | status | gstat
+    PPN_U8(gnode, 0) PPN_U8(lnode, this->G) PPN_U8(onode, this->G + this->L) PPN_U8(enode, this->G + this->L + this->N)
+    PPN_U8(status, this->G + this->L + 2 * this->N) PPN_U8(gstat, this->G + this->L + 3 * this->N)
+    PPN_U8(btype, 2 * this->G + this->L + 3 * this->N) PPN_U8(mark, 2 * this->G + this->L + 3 * this->N + this->NB)
+    PPN_U8(over, 2 * this->G + this->L + 3 * this->N + 2 * this->NB) PPN_U8(act, 2 * this->G + this->L + 4 * this->N + 2 * this->NB)
+    PPN_U8(subch, 2 * this->G + this->L + 4 * this->N + 2 * this->NB + this->A)
+    PPN_U8(ill, 2 * this->G + this->L + 4 * this->N + 2 * this->NB + this->A + this->S)
+#undef PPN_U8
+    __device__ __forceinline__ double* mat() const { return reinterpret_cast<double*>(base + fixed_bytes); }
+};
 
 // ------------------------------------------------------------------------------------------------- dense inverse
 // In-place Gauss-Jordan inverse without pivoting of the n x n matrix a (row stride ld, odd => conflict-free column
-// walks).  Rows are spread over lanes, columns over the warps of the env.  A zero/NaN pivot yields inf/NaN, which the
-// caller's mismatch test turns into "diverging" (the reference's splu raises on an exactly singular factor).
-template <int TPE, int MAXR> __device__ void gj_invert(double* a, int n, int ld, int tid) {
-    const int lane = tid & 31, w = tid >> 5, W = TPE / 32;
+// walks).  Rows are spread over the lanes of the group (TPE <= 32) or over lanes with columns over warps (CTA).
+// A zero/NaN pivot yields inf/NaN, which the caller's mismatch test turns into "diverging" (the reference's splu
+// raises on an exactly singular factor).
+template <int TPE, int MAXR> __device__ void gj_invert(double* a, int n, int ld, int tid, unsigned mask) {
+    constexpr int RW = TPE < 32 ? TPE : 32;                 // lanes that share the rows
+    constexpr int W = TPE <= 32 ? 1 : TPE / 32;             // column stripes
+    const int lane = TPE <= 32 ? tid : (tid & 31), w = TPE <= 32 ? 0 : (tid >> 5);
     for (int k = 0; k < n; k++) {
         const double p = 1.0 / a[k * ld + k];
         double cm[MAXR];
 #pragma unroll
         for (int r = 0; r < MAXR; r++) {
-            const int i = lane + 32 * r;
+            const int i = lane + RW * r;
             cm[r] = (i < n && i != k) ? a[i * ld + k] * p : 0.0;
         }
-        env_sync<TPE>();
+        env_sync<TPE>(mask);
 #pragma unroll
         for (int r = 0; r < MAXR; r++) {
-            const int i = lane + 32 * r;
+            const int i = lane + RW * r;
             if (i < n && i != k) {
                 const double ci = cm[r];
                 double* ai = a + i * ld;
                 const double* ak = a + k * ld;
-                for (int j = w; j < n; j += W)
-                    if (j != k) ai[j] = fma(-ci, ak[j], ai[j]);
+                for (int j = w; j < n; j += W) ai[j] = fma(-ci, ak[j], ai[j]);   // column k fixed just below
                 if (w == k % W) ai[k] = -ci;
             }
         }
-        env_sync<TPE>();
+        env_sync<TPE>(mask);
         for (int j = tid; j < n; j += TPE) a[k * ld + j] = (j == k) ? p : a[k * ld + j] * p;
-        env_sync<TPE>();
+        env_sync<TPE>(mask);
     }
 }
 
@@ -187,43 +199,45 @@ __device__ __forceinline__ int take_next_chronic(int* cursor, const PpnDevCfg& c
 
 // ------------------------------------------------------------------------------------------ topology-derived maps
 // Current bus of every element (sub + S*node) and normalize_prods_voltages' positional baseKV (grid.py:266-271).
-template <int TPE> __device__ void refresh_element_buses(Env<TPE>& e, const PpnDevCase& c) {
+template <int TPE, class D>
+__device__ __forceinline__ void refresh_element_buses(Env<TPE, D>& e, const PpnDevCase& c) {
     const int S = e.S;
     for (int l = e.tid; l < e.N; l += TPE) {
-        e.fbus[l] = (short)(c.lor_sub[l] + S * e.onode[l]);
-        e.tbus[l] = (short)(c.lex_sub[l] + S * e.enode[l]);
+        e.fbus()[l] = (short)(c.lor_sub[l] + S * e.onode()[l]);
+        e.tbus()[l] = (short)(c.lex_sub[l] + S * e.enode()[l]);
     }
-    for (int g = e.tid; g < e.G; g += TPE) e.gbus[g] = (short)(c.gen_sub[g] + S * e.gnode[g]);
-    for (int l = e.tid; l < e.L; l += TPE) e.lbus[l] = (short)(c.load_sub[l] + S * e.lnode[l]);
-    env_sync<TPE>();
+    for (int g = e.tid; g < e.G; g += TPE) e.gbus()[g] = (short)(c.gen_sub[g] + S * e.gnode()[g]);
+    for (int l = e.tid; l < e.L; l += TPE) e.lbus()[l] = (short)(c.load_sub[l] + S * e.lnode()[l]);
+    env_sync<TPE>(e.mask);
     // baseKV of gen-hosting buses in bus-array order, applied positionally to the generators
     for (int g = e.tid; g < e.G; g += TPE) {
-        const int b = e.gbus[g];
+        const int b = e.gbus()[g];
         int rank = 0;
-        for (int h = 0; h < e.G; h++) rank += (e.gbus[h] < b);
-        e.gkv[rank] = c.bus_basekv[b];
+        for (int h = 0; h < e.G; h++) rank += (e.gbus()[h] < b);
+        e.gkv()[rank] = c.bus_basekv[b];
     }
-    env_sync<TPE>();
+    env_sync<TPE>(e.mask);
 }
 
 // game.py:476-501 then :405-474 and grid.py:273-311.
-template <int TPE>
-__device__ void load_next_timestep(Env<TPE>& e, const PpnDevCase& c, const PpnDevChronics& ch, const PpnDevCfg& cfg,
+template <int TPE, class D>
+__device__ __forceinline__ void load_next_timestep(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevChronics& ch, const PpnDevCfg& cfg,
                                    bool is_sim, int env) {
-    int chronic = e.cursor[0], row = e.cursor[1];
+    int chronic = e.cursor()[0], row = e.cursor()[1];
     const int e_chronic = chronic, e_row = row;  // `current_timestep_entries` before the move (simulate reads its planned values)
-    env_sync<TPE>();
+    env_sync<TPE>(e.mask);
     int n_rows = ch.n_rows[chronic];
     bool at_last = (row >= 0 && row == n_rows - 1) || (row == -2 && ch.last_id_zero[chronic]);
     if (at_last && !is_sim) {
         if (e.tid == 0) {
-            e.cursor[0] = take_next_chronic(e.cursor, cfg, ch.n_chronics, env);
-            e.cursor[1] = -2;
+            e.cursor()[0] = take_next_chronic(e.cursor(), cfg, ch.n_chronics, env);
+            e.cursor()[1] = -2;
         }
-        env_sync<TPE>();
-        chronic = e.cursor[0];
+        env_sync<TPE>(e.mask);
+        chronic = e.cursor()[0];
         row = -2;
         n_rows = ch.n_rows[chronic];
+        env_sync<TPE>(e.mask);
     }
     int nrow;
     if (row == -1) nrow = 0;
@@ -231,11 +245,11 @@ __device__ void load_next_timestep(Env<TPE>& e, const PpnDevCase& c, const PpnDe
     else nrow = min(row + 1, n_rows - 1);
     if (!is_sim) {
         for (int i = e.tid; i < e.N; i += TPE) {
-            if (e.recon[i] > 0) e.recon[i] -= 1;
-            if (e.lreact[i] > 0) e.lreact[i] -= 1;
+            if (e.recon()[i] > 0) e.recon()[i] -= 1;
+            if (e.lreact()[i] > 0) e.lreact()[i] -= 1;
         }
         for (int i = e.tid; i < e.S; i += TPE)
-            if (e.nreact[i] > 0) e.nreact[i] -= 1;
+            if (e.nreact()[i] > 0) e.nreact()[i] -= 1;
     }
     const float* next = chronic_row(ch, chronic, nrow);
     const float* src;
@@ -248,392 +262,393 @@ __device__ void load_next_timestep(Env<TPE>& e, const PpnDevCase& c, const PpnDe
     }
     for (int g = e.tid; g < e.G; g += TPE) {
         const float pv = src[opv + g];
-        e.gpg[g] = (double)src[opp + g];
-        e.gvg[g] = (double)(pv <= 0.f ? 0.f : pv) / e.gkv[g];
-        e.gstat[g] = pv > 0.f ? 1 : 0;
+        e.gpg()[g] = (double)src[opp + g];
+        e.gvg()[g] = (double)(pv <= 0.f ? 0.f : pv) / e.gkv()[g];
+        e.gstat()[g] = pv > 0.f ? 1 : 0;
     }
     for (int l = e.tid; l < e.L; l += TPE) {
-        e.lpd[l] = (double)src[olp + l];
-        e.lqd[l] = (double)src[olq + l];
+        e.lpd()[l] = (double)src[olp + l];
+        e.lqd()[l] = (double)src[olq + l];
     }
-    env_sync<TPE>();  // counters decremented before the maxima below
-    for (int i = e.tid; i < e.N; i += TPE) {
+    for (int i = e.tid; i < e.N; i += TPE) {   // same lane decremented recon[i] above
         const int m = (int)next[ch.o_mt + i];
-        if (m > 0) { e.status[i] = 0; e.recon[i] = max(e.recon[i], m); }
+        if (m > 0) { e.status()[i] = 0; e.recon()[i] = max(e.recon()[i], m); }
         if (!is_sim) {
             const int h = (int)next[ch.o_hz + i];
-            if (h > 0) { e.status[i] = 0; e.recon[i] = max(e.recon[i], h); }
+            if (h > 0) { e.status()[i] = 0; e.recon()[i] = max(e.recon()[i], h); }
         }
     }
     if (e.tid == 0) {
-        e.cursor[0] = chronic; e.cursor[1] = nrow;
+        e.cursor()[0] = chronic; e.cursor()[1] = nrow;
         // row whose planned values the observation reports (`current_timestep_entries`: not moved by simulate)
-        e.misc[6] = is_sim ? e_chronic : chronic;
-        e.misc[7] = is_sim ? max(e_row, 0) : nrow;
+        e.misc()[6] = is_sim ? e_chronic : chronic;
+        e.misc()[7] = is_sim ? max(e_row, 0) : nrow;
     }
-    env_sync<TPE>();
+    env_sync<TPE>(e.mask);
 }
 
 // ----------------------------------------------------------------------------------------------------- load-flow
 // isolated buses (grid.py:176-210): mark[b] = 1 when no in-service line ends at b
-template <int TPE> __device__ void compute_isolated(Env<TPE>& e) {
-    for (int b = e.tid; b < e.NB; b += TPE) e.mark[b] = 1;
-    env_sync<TPE>();
+template <int TPE, class D>
+__device__ __forceinline__ void compute_isolated(Env<TPE, D>& e) {
+    for (int b = e.tid; b < e.NB; b += TPE) e.mark()[b] = 1;
+    env_sync<TPE>(e.mask);
     for (int l = e.tid; l < e.N; l += TPE)
-        if (e.status[l]) { e.mark[e.fbus[l]] = 0; e.mark[e.tbus[l]] = 0; }
-    env_sync<TPE>();
+        if (e.status()[l]) { e.mark()[e.fbus()[l]] = 0; e.mark()[e.tbus()[l]] = 0; }
+    env_sync<TPE>(e.mask);
 }
 
-// S_b = V_b conj(sum_j Y_bj V_j) for bus b, gathering over the lines of its substation.
-template <int TPE>
-__device__ __forceinline__ void bus_power(const Env<TPE>& e, const PpnDevCase& c, int b, double& sr, double& si) {
-    const int S = e.S;
-    const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
-    const double vr = e.vr[b], vi = e.vi[b];
-    const double yr = c.bus_ysh_r[b], yi = c.bus_ysh_i[b];
-    double ir = yr * vr - yi * vi, ii = yr * vi + yi * vr;
-    for (int k = c.adj_ptr[s]; k < c.adj_ptr[s + 1]; k++) {
+// Line-end entries in the static substation adjacency order (c.adj): ebus[k] = bus this end sits on, or -1 when the
+// line is out of service; eoth[k] = bus of the other end.  A bus then walks the entries of its substation.
+template <int TPE, class D>
+__device__ __forceinline__ void build_entries(Env<TPE, D>& e, const PpnDevCase& c) {
+    for (int k = e.tid; k < 2 * e.N; k += TPE) {
         const int a = c.adj[k], l = a >> 1, end = a & 1;
-        if (!e.status[l]) continue;
-        const double* y = c.line_y + 8 * l;
-        if (end == 0) {
-            if (e.onode[l] != node) continue;
-            const int o = e.tbus[l];
-            const double wr = e.vr[o], wi = e.vi[o];
-            ir += y[0] * vr - y[1] * vi + y[2] * wr - y[3] * wi;
-            ii += y[0] * vi + y[1] * vr + y[2] * wi + y[3] * wr;
-        } else {
-            if (e.enode[l] != node) continue;
-            const int o = e.fbus[l];
-            const double wr = e.vr[o], wi = e.vi[o];
-            ir += y[6] * vr - y[7] * vi + y[4] * wr - y[5] * wi;
-            ii += y[6] * vi + y[7] * vr + y[4] * wi + y[5] * wr;
-        }
+        const bool on = e.status()[l] != 0;
+        e.ebus()[k] = on ? (end == 0 ? e.fbus()[l] : e.tbus()[l]) : (short)-1;
+        e.eoth()[k] = end == 0 ? e.tbus()[l] : e.fbus()[l];
+    }
+    env_sync<TPE>(e.mask);
+}
+
+// S_b = V_b conj((Ybus V)_b), gathered per bus: diagonal term (ydr, ydi: shunt + own-end admittances) + the
+// off-diagonal entries of the in-service lines that end on this bus.
+template <int TPE, class D>
+__device__ __forceinline__ void bus_power(const Env<TPE, D>& e, const PpnDevCase& c, int b, double& sr, double& si) {
+    const int s = b >= e.S ? b - e.S : b;
+    const double vr = e.vr()[b], vi = e.vi()[b];
+    double ir = e.ydr()[b] * vr - e.ydi()[b] * vi, ii = e.ydr()[b] * vi + e.ydi()[b] * vr;
+    const int k1 = c.adj_ptr[s + 1];
+    for (int k = c.adj_ptr[s]; k < k1; k++) {
+        if (e.ebus()[k] != b) continue;
+        const int a = c.adj[k];
+        const double* y = c.line_y + 8 * (a >> 1) + ((a & 1) ? 4 : 2);   // ytf or yft
+        const int o = e.eoth()[k];
+        const double wr = e.vr()[o], wi = e.vi()[o];
+        ir = fma(y[0], wr, fma(-y[1], wi, ir));
+        ii = fma(y[0], wi, fma(y[1], wr, ii));
     }
     sr = vr * ir + vi * ii;   // V conj(I)
     si = vi * ir - vr * ii;
 }
 
+// demand at bus b: the load of the substation when it sits on this node (its sister bus carries none)
+template <int TPE, class D>
+__device__ __forceinline__ void bus_demand(const Env<TPE, D>& e, const PpnDevCase& c, int b, double& pd, double& qd) {
+    const int s = b >= e.S ? b - e.S : b, node = b >= e.S ? 1 : 0;
+    const int l = c.load_of_sub[s];
+    const bool here = l >= 0 && e.lnode()[l] == node;
+    pd = here ? e.lpd()[l] : 0.0;
+    qd = here ? e.lqd()[l] : 0.0;
+}
+
 // fdpf's mismatch: mis = (V conj(Ybus V) - Sbus)/Vm; P over pv+pq, Q over pq; returns the two infinity norms.
-template <int TPE>
-__device__ void mismatch(Env<TPE>& e, const PpnDevCase& c, double& nP, double& nQ) {
+template <int TPE, class D>
+__device__ __forceinline__ void mismatch(Env<TPE, D>& e, const PpnDevCase& c, double& nP, double& nQ) {
     double mp = 0.0, mq = 0.0;
     for (int b = e.tid; b < e.NB; b += TPE) {
-        const int t = e.btype[b];
-        if (t == PPN_BT_ISOLATED) continue;
+        const int t = e.btype()[b];
+        if (t == PPN_BT_ISOLATED || t == PPN_BT_REF) continue;
         double sr, si;
         bus_power(e, c, b, sr, si);
-        e.sr[b] = sr; e.si[b] = si;
-        if (t != PPN_BT_REF) {
-            const double vm = e.vm[b];
-            const double p = (sr - e.pin[b]) / vm;
-            e.P[e.idxp[b]] = p;
-            const double ap = fabs(p);
-            mp = (ap > mp || ap != ap) ? ap : mp;
-            if (t == PPN_BT_PQ) {
-                const double q = (si - e.qin[b]) / vm;
-                e.Q[e.idxq[b]] = q;
-                const double aq = fabs(q);
-                mq = (aq > mq || aq != aq) ? aq : mq;
-            }
+        const double vm = e.vm()[b];
+        const double p = (sr - e.pin()[b]) / vm;
+        e.P()[e.idxp()[b]] = p;
+        const double ap = fabs(p);
+        mp = (ap > mp || ap != ap) ? ap : mp;
+        if (t == PPN_BT_PQ) {
+            const double q = (si - e.qin()[b]) / vm;
+            e.Q()[e.idxq()[b]] = q;
+            const double aq = fabs(q);
+            mq = (aq > mq || aq != aq) ? aq : mq;
         }
     }
-    nP = env_max_nan<TPE>(mp, e.redd, e.tid);
-    nQ = env_max_nan<TPE>(mq, e.redd + TPE / 32, e.tid);
-    env_sync<TPE>();
+    nP = env_max_nan<TPE>(mp, e.redd(), e.tid, e.mask);
+    nQ = env_max_nan<TPE>(mq, e.redd() + (TPE + 31) / 32, e.tid, e.mask);
+    env_sync<TPE>(e.mask);
 }
 
 // One load-flow on the current topology/injections (grid.py:244-264 around runpf / rundcpf).  Returns true when the
 // reference raises DivergingLoadflowException.  On success the state (vm, va in degrees, gen pg/qg, flows) is the
 // adopted output (`self.mpc = output`, grid.py:260).
-template <int TPE, int MAXR>
-__device__ bool loadflow(Env<TPE>& e, const PpnDevCase& c, const PpnDevCfg& cfg, const PpnStepArgs& args, int slot,
+template <int TPE, int MAXR, class D>
+__device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevCfg& cfg, const PpnStepArgs& args, int slot,
                          int& n_iter) {
     const int NB = e.NB, S = e.S, tid = e.tid;
+    const unsigned mask = e.mask;
     n_iter = 0;
     compute_isolated(e);  // mark = isolated
-    // ---- _synchronize_bus_types (grid.py:140-174): provisional types in btype: 4->ISOLATED, 1 PQ, 2 PV, 3 REF
+    // ---- _synchronize_bus_types (grid.py:140-174) folded with bustypes: a bus whose generator is off is PQ
     int slack = c.slack_bus;
-    if (e.mark[slack]) {
+    if (e.mark()[slack]) {
         int found = -1;
         for (int g = 0; g < e.G; g++)
-            if (e.gbus[g] != c.slack_bus) { found = e.gbus[g]; break; }
+            if (e.gbus()[g] != c.slack_bus) { found = e.gbus()[g]; break; }
         slack = found;
     }
     for (int b = tid; b < NB; b += TPE) {
         const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
         const int g = c.gen_of_sub[s];
-        const bool has_gen = g >= 0 && e.gnode[g] == node;
-        int t = e.mark[b] ? PPN_BT_ISOLATED : (has_gen ? PPN_BT_PV : PPN_BT_PQ);
-        if (b == slack && !e.mark[b] && has_gen) t = PPN_BT_REF;
-        // bustypes: a bus whose generator is off is PQ, whatever its type column says
-        const bool on_gen = has_gen && e.gstat[g] > 0;
+        const bool has_gen = g >= 0 && e.gnode()[g] == node;
+        int t = e.mark()[b] ? PPN_BT_ISOLATED : (has_gen ? PPN_BT_PV : PPN_BT_PQ);
+        if (b == slack && !e.mark()[b] && has_gen) t = PPN_BT_REF;
+        const bool on_gen = has_gen && e.gstat()[g] > 0;
         if (t != PPN_BT_ISOLATED && !on_gen) t = PPN_BT_PQ;
-        e.btype[b] = (uint8_t)t;
+        e.btype()[b] = (uint8_t)t;
     }
-    env_sync<TPE>();
-    // ---- bustypes: reference bus, compact indices (warp 0 scans the buses in bus-array order)
-    if (tid < 32) {
+    env_sync<TPE>(mask);
+    // ---- bustypes: reference bus, compact indices (the group's first warp scans the buses in bus-array order)
+    if (TPE <= 32 || tid < 32) {
+        constexpr int CH = TPE < 32 ? TPE : 32;
+        const unsigned gm = TPE <= 32 ? mask : PPN_FULL;
+        const int sh = TPE <= 32 ? e.shift : 0;
+        const int ln = TPE <= 32 ? tid : (tid & 31);
+        const unsigned chm = CH == 32 ? 0xffffffffu : ((1u << CH) - 1u);
         int ref = -1, firstpv = -1, np_ = 0, nq_ = 0;
-        for (int base = 0; base < NB; base += 32) {
-            const int b = base + tid;
-            const int t = b < NB ? e.btype[b] : PPN_BT_ISOLATED;
-            const unsigned mr = __ballot_sync(PPN_FULL, t == PPN_BT_REF);
-            const unsigned mv = __ballot_sync(PPN_FULL, t == PPN_BT_PV);
+        for (int base = 0; base < NB; base += CH) {
+            const int b = base + ln;
+            const int t = b < NB ? e.btype()[b] : PPN_BT_ISOLATED;
+            const unsigned mr = (__ballot_sync(gm, t == PPN_BT_REF) >> sh) & chm;
+            const unsigned mv = (__ballot_sync(gm, t == PPN_BT_PV) >> sh) & chm;
             if (ref < 0 && mr) ref = base + __ffs(mr) - 1;
             if (firstpv < 0 && mv) firstpv = base + __ffs(mv) - 1;
         }
         if (ref < 0) ref = firstpv;  // ref = pv[0] (IndexError in PYPOWER when there is none)
-        if (ref >= 0 && tid == 0) e.btype[ref] = PPN_BT_REF;
-        __syncwarp();
-        for (int base = 0; base < NB; base += 32) {
-            const int b = base + tid;
-            const int t = b < NB ? e.btype[b] : PPN_BT_ISOLATED;
+        if (ref >= 0 && ln == 0) e.btype()[ref] = PPN_BT_REF;
+        __syncwarp(gm);
+        for (int base = 0; base < NB; base += CH) {
+            const int b = base + ln;
+            const int t = b < NB ? e.btype()[b] : PPN_BT_ISOLATED;
             const bool inp = (t == PPN_BT_PV || t == PPN_BT_PQ), inq = (t == PPN_BT_PQ);
-            const unsigned mp = __ballot_sync(PPN_FULL, inp), mq = __ballot_sync(PPN_FULL, inq);
-            const unsigned lt = (1u << tid) - 1u;
-            if (inp) { const int i = np_ + __popc(mp & lt); e.idxp[b] = (short)i; e.busp[i] = (short)b; }
-            if (inq) { const int i = nq_ + __popc(mq & lt); e.idxq[b] = (short)i; e.busq[i] = (short)b; }
+            const unsigned mp = (__ballot_sync(gm, inp) >> sh) & chm, mq = (__ballot_sync(gm, inq) >> sh) & chm;
+            const unsigned lt = (1u << ln) - 1u;
+            if (inp) { const int i = np_ + __popc(mp & lt); e.idxp()[b] = (short)i; e.busp()[i] = (short)b; }
+            if (inq) { const int i = nq_ + __popc(mq & lt); e.idxq()[b] = (short)i; e.busq()[i] = (short)b; }
             np_ += __popc(mp); nq_ += __popc(mq);
         }
-        if (tid == 0) { e.misc[0] = ref; e.misc[1] = np_; e.misc[2] = nq_; }
+        if (ln == 0) { e.misc()[0] = ref; e.misc()[1] = np_; e.misc()[2] = nq_; }
     }
-    env_sync<TPE>();
-    const int ref = e.misc[0], n1 = e.misc[1], n2 = e.misc[2];
+    env_sync<TPE>(mask);
+    const int ref = e.misc()[0], n1 = e.misc()[1], n2 = e.misc()[2];
     if (ref < 0) return true;
     // ---- connectivity: every non-isolated bus must be reachable from the reference bus over in-service lines
-    for (int b = tid; b < NB; b += TPE) e.mark[b] = (b == ref) ? 1 : 0;   // mark = reached
-    env_sync<TPE>();
+    for (int b = tid; b < NB; b += TPE) e.mark()[b] = (b == ref) ? 1 : 0;   // mark = reached
+    env_sync<TPE>(mask);
     while (true) {
         bool changed = false;
         for (int l = tid; l < e.N; l += TPE) {
-            if (!e.status[l]) continue;
-            const int f = e.fbus[l], t = e.tbus[l];
-            const int rf = e.mark[f], rt = e.mark[t];
-            if (rf != rt) { e.mark[f] = 1; e.mark[t] = 1; changed = true; }
+            if (!e.status()[l]) continue;
+            const int f = e.fbus()[l], t = e.tbus()[l];
+            const int rf = e.mark()[f], rt = e.mark()[t];
+            if (rf != rt) { e.mark()[f] = 1; e.mark()[t] = 1; changed = true; }
         }
-        if (!env_any<TPE>(changed)) break;
-        env_sync<TPE>();
+        if (!env_any<TPE>(changed, mask)) break;
+        env_sync<TPE>(mask);
     }
-    env_sync<TPE>();
+    env_sync<TPE>(mask);
     bool floating = false;
-    for (int b = tid; b < NB; b += TPE) floating |= (e.btype[b] != PPN_BT_ISOLATED && !e.mark[b]);
+    for (int b = tid; b < NB; b += TPE) floating |= (e.btype()[b] != PPN_BT_ISOLATED && !e.mark()[b]);
     // generators that are out of service (off, or on an isolated bus) end every adopted load-flow with Pg = Qg = 0
-    const bool any_floating = env_any<TPE>(floating);
-    if (any_floating) {
+    if (env_any<TPE>(floating, mask)) {
         for (int g = tid; g < e.G; g += TPE)
-            if (!(e.gstat[g] > 0 && e.btype[e.gbus[g]] != PPN_BT_ISOLATED)) { e.gpg[g] = 0.0; e.gqg[g] = 0.0; }
-        env_sync<TPE>();
+            if (!(e.gstat()[g] > 0 && e.btype()[e.gbus()[g]] != PPN_BT_ISOLATED)) { e.gpg()[g] = 0.0; e.gqg()[g] = 0.0; }
+        env_sync<TPE>(mask);
         return true;
     }
     if (n1 == 0 || (n2 == 0 && !cfg.dc)) return true;
     // ---- per-bus demand and makeSbus
-    for (int b = tid; b < NB; b += TPE) { e.pdb[b] = 0.0; e.qdb[b] = 0.0; }
-    env_sync<TPE>();
-    for (int l = tid; l < e.L; l += TPE) { e.pdb[e.lbus[l]] = e.lpd[l]; e.qdb[e.lbus[l]] = e.lqd[l]; }
-    env_sync<TPE>();
+    build_entries(e, c);
     for (int b = tid; b < NB; b += TPE) {
-        if (e.btype[b] == PPN_BT_ISOLATED) continue;
+        if (e.btype()[b] == PPN_BT_ISOLATED) continue;
         const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
         const int g = c.gen_of_sub[s];
-        const bool on_gen = g >= 0 && e.gnode[g] == node && e.gstat[g] > 0;
-        double p = -e.pdb[b], q = -e.qdb[b];
-        if (on_gen) { p += e.gpg[g]; q += e.gqg[g]; }
-        e.pin[b] = p / c.base_mva;
-        e.qin[b] = q / c.base_mva;
+        const bool on_gen = g >= 0 && e.gnode()[g] == node && e.gstat()[g] > 0;
+        double pd, qd;
+        bus_demand(e, c, b, pd, qd);
+        double p = -pd, q = -qd;
+        if (on_gen) { p += e.gpg()[g]; q += e.gqg()[g]; }
+        e.pin()[b] = p / c.base_mva;
+        e.qin()[b] = q / c.base_mva;
     }
     // ---- matrices: shared memory when they fit, else the env's slice of the global workspace
     const int ld1 = n1 | 1, ld2 = n2 | 1;
     double *M1, *M2;
-    if (n1 * ld1 + n2 * ld2 <= args.mat_cap) { M1 = e.mat; M2 = e.mat + n1 * ld1; }
+    if (n1 * ld1 + n2 * ld2 <= args.mat_cap) { M1 = e.mat(); M2 = M1 + n1 * ld1; }
     else { M1 = args.ws + (size_t)slot * args.ws_stride; M2 = M1 + n1 * ld1; }
     bool success;
     if (cfg.dc) {
         // ================= rundcpf: B theta = Pbus on pv+pq, Vm := 1
         for (int i = tid; i < n1 * ld1; i += TPE) M1[i] = 0.0;
-        env_sync<TPE>();
+        env_sync<TPE>(mask);
+        const double va_ref = e.va()[ref] * (PPN_PI / 180.0);
         for (int i = tid; i < n1; i += TPE) {
-            const int b = e.busp[i];
-            const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
-            double diag = 0.0;
+            const int b = e.busp()[i];
+            const int s = b >= S ? b - S : b;
+            double diag = 0.0, bref = 0.0;
             for (int k = c.adj_ptr[s]; k < c.adj_ptr[s + 1]; k++) {
-                const int a = c.adj[k], l = a >> 1, end = a & 1;
-                if (!e.status[l]) continue;
-                if ((end == 0 ? e.onode[l] : e.enode[l]) != node) continue;
-                const int o = end == 0 ? e.tbus[l] : e.fbus[l];
-                const double w = c.line_bdc[l];
+                if (e.ebus()[k] != b) continue;
+                const int o = e.eoth()[k];
+                const double w = c.line_bdc[c.adj[k] >> 1];
                 diag += w;
-                if (o != ref) M1[i * ld1 + e.idxp[o]] -= w;
+                if (o != ref) M1[i * ld1 + e.idxp()[o]] -= w; else bref -= w;
             }
             M1[i * ld1 + i] += diag;
+            // rhs = Pbus[pvpq] - B[pvpq, ref] Va0[ref], Pbus = Re(Sbus) - Gs/baseMVA
+            e.P()[i] = (e.pin()[b] - c.bus_ysh_r[b]) - bref * va_ref;
         }
-        env_sync<TPE>();
-        gj_invert<TPE, MAXR>(M1, n1, ld1, tid);
-        // rhs = Pbus[pvpq] - B[pvpq, ref] Va0[ref], Pbus = Re(Sbus) - Gs/baseMVA
-        const double va_ref = e.va[ref] * (PPN_PI / 180.0);
-        for (int i = tid; i < n1; i += TPE) {
-            const int b = e.busp[i];
-            const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
-            double bref = 0.0;
-            for (int k = c.adj_ptr[s]; k < c.adj_ptr[s + 1]; k++) {
-                const int a = c.adj[k], l = a >> 1, end = a & 1;
-                if (!e.status[l]) continue;
-                if ((end == 0 ? e.onode[l] : e.enode[l]) != node) continue;
-                const int o = end == 0 ? e.tbus[l] : e.fbus[l];
-                if (o == ref) bref -= c.line_bdc[l];
-            }
-            e.P[i] = (e.pin[b] - c.bus_ysh_r[b]) - bref * va_ref;
-        }
-        env_sync<TPE>();
+        env_sync<TPE>(mask);
+        gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
         for (int i = tid; i < n1; i += TPE) {
             double acc = 0.0;
-            for (int j = 0; j < n1; j++) acc = fma(M1[i * ld1 + j], e.P[j], acc);
-            e.Q[i] = acc;  // theta (radians) of pvpq bus i
+            for (int j = 0; j < n1; j++) acc = fma(M1[i * ld1 + j], e.P()[j], acc);
+            e.Q()[i] = acc;  // theta (radians) of pvpq bus i
         }
-        env_sync<TPE>();
+        env_sync<TPE>(mask);
         for (int b = tid; b < NB; b += TPE) {
-            const int t = e.btype[b];
+            const int t = e.btype()[b];
             if (t == PPN_BT_ISOLATED) continue;
-            e.vr[b] = (t == PPN_BT_REF) ? va_ref : e.Q[e.idxp[b]];  // vr holds theta in DC mode
+            e.vr()[b] = (t == PPN_BT_REF) ? va_ref : e.Q()[e.idxp()[b]];  // vr holds theta in DC mode
         }
-        env_sync<TPE>();
+        env_sync<TPE>(mask);
         // branch flows, slack production
         for (int l = tid; l < e.N; l += TPE) {
             double p = 0.0;
-            if (e.status[l]) p = c.line_bdc[l] * (e.vr[e.fbus[l]] - e.vr[e.tbus[l]]) * c.base_mva;
-            e.pf[l] = p; e.pt[l] = -p; e.qf[l] = 0.0; e.qt[l] = 0.0;
+            if (e.status()[l]) p = c.line_bdc[l] * (e.vr()[e.fbus()[l]] - e.vr()[e.tbus()[l]]) * c.base_mva;
+            e.pf()[l] = p; e.pt()[l] = -p; e.qf()[l] = 0.0; e.qt()[l] = 0.0;
         }
         if (tid == 0) {
             // gen[refgen, PG] += (B[ref, :] Va - Pbus[ref]) baseMVA
-            const int s = ref >= S ? ref - S : ref, node = ref >= S ? 1 : 0;
+            const int s = ref >= S ? ref - S : ref;
             double acc = 0.0;
             for (int k = c.adj_ptr[s]; k < c.adj_ptr[s + 1]; k++) {
-                const int a = c.adj[k], l = a >> 1, end = a & 1;
-                if (!e.status[l]) continue;
-                if ((end == 0 ? e.onode[l] : e.enode[l]) != node) continue;
-                const int o = end == 0 ? e.tbus[l] : e.fbus[l];
-                acc += c.line_bdc[l] * (e.vr[ref] - e.vr[o]);
+                if (e.ebus()[k] != ref) continue;
+                acc += c.line_bdc[c.adj[k] >> 1] * (e.vr()[ref] - e.vr()[e.eoth()[k]]);
             }
             const int g = c.gen_of_sub[s];
-            e.gpg[g] = e.gpg[g] + (acc - (e.pin[ref] - c.bus_ysh_r[ref])) * c.base_mva;
+            e.gpg()[g] = e.gpg()[g] + (acc - (e.pin()[ref] - c.bus_ysh_r[ref])) * c.base_mva;
         }
-        env_sync<TPE>();
+        env_sync<TPE>(mask);
         for (int b = tid; b < NB; b += TPE) {
-            if (e.btype[b] == PPN_BT_ISOLATED) continue;
-            e.vm[b] = 1.0;
-            e.va[b] = e.vr[b] * (180.0 / PPN_PI);
+            if (e.btype()[b] == PPN_BT_ISOLATED) continue;
+            e.vm()[b] = 1.0;
+            e.va()[b] = e.vr()[b] * (180.0 / PPN_PI);
         }
         success = true;
     } else {
         // ================= runpf, PF_ALG=2 (fast-decoupled XB)
         // V0 from the stored state; on-line generators impose their set-point magnitude
         for (int b = tid; b < NB; b += TPE) {
-            if (e.btype[b] == PPN_BT_ISOLATED) continue;
+            if (e.btype()[b] == PPN_BT_ISOLATED) continue;
             double sn, cs;
-            sincos(e.va[b] * (PPN_PI / 180.0), &sn, &cs);
-            double vr = e.vm[b] * cs, vi = e.vm[b] * sn;
+            sincos(e.va()[b] * (PPN_PI / 180.0), &sn, &cs);
+            double vr = e.vm()[b] * cs, vi = e.vm()[b] * sn;
             const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
             const int g = c.gen_of_sub[s];
-            if (g >= 0 && e.gnode[g] == node && e.gstat[g] > 0) {
-                const double sc = e.gvg[g] / hypot(vr, vi);
+            if (g >= 0 && e.gnode()[g] == node && e.gstat()[g] > 0) {
+                const double sc = e.gvg()[g] / hypot(vr, vi);
                 vr *= sc; vi *= sc;
             }
-            e.vr[b] = vr; e.vi[b] = vi;
-            e.vm[b] = hypot(vr, vi);        // fdpf: Vm = abs(V0), Va = angle(V0)
-            e.va[b] = atan2(vi, vr);        // radians from here on
+            e.vr()[b] = vr; e.vi()[b] = vi;
+            const double vm = hypot(vr, vi);   // fdpf: Vm = abs(V0), Va = angle(V0)
+            e.vm()[b] = vm;
+            e.va()[b] = atan2(vi, vr);           // radians from here on
+            e.cs()[b] = cs; e.sn()[b] = sn;        // unit phasor of the current angle (refreshed by the P iteration)
         }
-        // B' (r = 0, no charging, no shunts, unit taps) over pv+pq; B'' = -Im(Ybus) over pq
+        // B' (r = 0, no charging, no shunts, unit taps) over pv+pq; B'' = -Im(Ybus) over pq; Ybus diagonal
         for (int i = tid; i < n1 * ld1 + n2 * ld2; i += TPE) M1[i] = 0.0;
-        env_sync<TPE>();
-        for (int i = tid; i < n1; i += TPE) {
-            const int b = e.busp[i];
-            const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
-            const bool ispq = e.btype[b] == PPN_BT_PQ;
-            const int iq = ispq ? e.idxq[b] : 0;
-            double d1 = 0.0, d2 = -c.bus_ysh_i[b];
+        env_sync<TPE>(mask);
+        for (int b = tid; b < NB; b += TPE) {
+            const int t = e.btype()[b];
+            if (t == PPN_BT_ISOLATED) continue;
+            const int s = b >= S ? b - S : b;
+            const bool ispq = t == PPN_BT_PQ, inp = t != PPN_BT_REF;
+            const int i = inp ? e.idxp()[b] : 0, iq = ispq ? e.idxq()[b] : 0;
+            double d1 = 0.0, yr = c.bus_ysh_r[b], yi = c.bus_ysh_i[b];
             for (int k = c.adj_ptr[s]; k < c.adj_ptr[s + 1]; k++) {
+                if (e.ebus()[k] != b) continue;
                 const int a = c.adj[k], l = a >> 1, end = a & 1;
-                if (!e.status[l]) continue;
-                if ((end == 0 ? e.onode[l] : e.enode[l]) != node) continue;
-                const int o = end == 0 ? e.tbus[l] : e.fbus[l];
+                const int o = e.eoth()[k];
                 const double w = c.line_bp[l];
                 const double* y = c.line_y + 8 * l;
+                yr += end == 0 ? y[0] : y[6];
+                yi += end == 0 ? y[1] : y[7];
                 d1 += w;
-                const int to = e.btype[o];
-                if (to != PPN_BT_REF) M1[i * ld1 + e.idxp[o]] -= w;
-                if (ispq) {
-                    d2 -= (end == 0 ? y[1] : y[7]);
-                    if (to == PPN_BT_PQ) M2[iq * ld2 + e.idxq[o]] -= (end == 0 ? y[3] : y[5]);
+                const int to = e.btype()[o];
+                if (inp && to != PPN_BT_REF) M1[i * ld1 + e.idxp()[o]] -= w;
+                if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= (end == 0 ? y[3] : y[5]);
+            }
+            e.ydr()[b] = yr; e.ydi()[b] = yi;
+            if (inp) M1[i * ld1 + i] += d1;
+            if (ispq) M2[iq * ld2 + iq] += -yi;
+        }
+        env_sync<TPE>(mask);
+        // fdpf: evaluate, then alternate P (angle) and Q (magnitude) half-iterations, testing after each
+        success = false;
+        int half = 0;
+        while (true) {
+            if (half > 0) {
+                if (half & 1) {   // P iteration: Va[pvpq] -= B'^-1 P
+                    for (int i = tid; i < n1; i += TPE) {
+                        double acc = 0.0;
+                        const double* mi = M1 + i * ld1;
+                        for (int j = 0; j < n1; j++) acc = fma(mi[j], e.P()[j], acc);
+                        const int b = e.busp()[i];
+                        const double va = e.va()[b] - acc;
+                        double sn, cs;
+                        sincos(va, &sn, &cs);
+                        e.va()[b] = va; e.cs()[b] = cs; e.sn()[b] = sn;
+                        e.vr()[b] = e.vm()[b] * cs; e.vi()[b] = e.vm()[b] * sn;
+                    }
+                } else {          // Q iteration: Vm[pq] -= B''^-1 Q
+                    for (int i = tid; i < n2; i += TPE) {
+                        double acc = 0.0;
+                        const double* mi = M2 + i * ld2;
+                        for (int j = 0; j < n2; j++) acc = fma(mi[j], e.Q()[j], acc);
+                        const int b = e.busq()[i];
+                        const double vm = e.vm()[b] - acc;
+                        e.vm()[b] = vm;
+                        e.vr()[b] = vm * e.cs()[b]; e.vi()[b] = vm * e.sn()[b];
+                    }
                 }
+                env_sync<TPE>(mask);
             }
-            M1[i * ld1 + i] += d1;
-            if (ispq) M2[iq * ld2 + iq] += d2;
-        }
-        env_sync<TPE>();
-        double nP, nQ;
-        mismatch(e, c, nP, nQ);
-        success = (nP < cfg.tol) && (nQ < cfg.tol);
-        if (!success) {
-            gj_invert<TPE, MAXR>(M1, n1, ld1, tid);
-            gj_invert<TPE, MAXR>(M2, n2, ld2, tid);
-        }
-        int it = 0;
-        while (!success && it < cfg.max_it) {
-            it++;
-            // P iteration: Va[pvpq] -= B'^-1 P
-            for (int i = tid; i < n1; i += TPE) {
-                double acc = 0.0;
-                const double* mi = M1 + i * ld1;
-                for (int j = 0; j < n1; j++) acc = fma(mi[j], e.P[j], acc);
-                const int b = e.busp[i];
-                const double va = e.va[b] - acc;
-                double sn, cs;
-                sincos(va, &sn, &cs);
-                e.va[b] = va;
-                e.vr[b] = e.vm[b] * cs; e.vi[b] = e.vm[b] * sn;
-            }
-            env_sync<TPE>();
+            double nP, nQ;
             mismatch(e, c, nP, nQ);
             if (nP < cfg.tol && nQ < cfg.tol) { success = true; break; }
-            // Q iteration: Vm[pq] -= B''^-1 Q
-            for (int i = tid; i < n2; i += TPE) {
-                double acc = 0.0;
-                const double* mi = M2 + i * ld2;
-                for (int j = 0; j < n2; j++) acc = fma(mi[j], e.Q[j], acc);
-                const int b = e.busq[i];
-                const double vm = e.vm[b] - acc;
-                double sn, cs;
-                sincos(e.va[b], &sn, &cs);
-                e.vm[b] = vm;
-                e.vr[b] = vm * cs; e.vi[b] = vm * sn;
+            if (half == 2 * cfg.max_it) break;
+            if (half == 0) {
+                gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
+                gj_invert<TPE, MAXR>(M2, n2, ld2, tid, mask);
             }
-            env_sync<TPE>();
-            mismatch(e, c, nP, nQ);
-            if (nP < cfg.tol && nQ < cfg.tol) { success = true; break; }
+            half++;
         }
+        const int it = (half + 1) / 2;
         n_iter = it;
         // ---- pfsoln
         int n_on = 0;
-        for (int g = tid; g < e.G; g += TPE) n_on += (e.gstat[g] > 0 && e.btype[e.gbus[g]] != PPN_BT_ISOLATED);
-        n_on = env_sum_int<TPE>(n_on, e.redi, tid);
+        for (int g = tid; g < e.G; g += TPE) n_on += (e.gstat()[g] > 0 && e.btype()[e.gbus()[g]] != PPN_BT_ISOLATED);
+        n_on = env_sum_int<TPE>(n_on, e.redi(), tid, mask);
         for (int g = tid; g < e.G; g += TPE) {
-            const int b = e.gbus[g];
-            if (e.gstat[g] > 0 && e.btype[b] != PPN_BT_ISOLATED) {
-                double q = e.si[b] * c.base_mva + e.qdb[b];
+            const int b = e.gbus()[g];
+            if (e.gstat()[g] > 0 && e.btype()[b] != PPN_BT_ISOLATED) {
+                double sr, si, pd, qd;
+                bus_power(e, c, b, sr, si);
+                bus_demand(e, c, b, pd, qd);
+                double q = si * c.base_mva + qd;
                 if (n_on > 1) {
                     const double qmin = c.gen_qmin[g], qmax = c.gen_qmax[g];
                     if (qmin != qmax) q = qmin + ((q - qmin) / (qmax - qmin + 2.220446049250313e-16)) * (qmax - qmin);
                 }
-                e.gqg[g] = q;
-                if (b == ref) e.gpg[g] = e.sr[b] * c.base_mva + e.pdb[b];
+                e.gqg()[g] = q;
+                if (b == ref) e.gpg()[g] = sr * c.base_mva + pd;
             }
         }
         for (int l = tid; l < e.N; l += TPE) {
             double pf = 0.0, qf = 0.0, pt = 0.0, qt = 0.0;
-            if (e.status[l]) {
+            if (e.status()[l]) {
                 const double* y = c.line_y + 8 * l;
-                const int f = e.fbus[l], t = e.tbus[l];
-                const double fr = e.vr[f], fi = e.vi[f], tr = e.vr[t], ti = e.vi[t];
+                const int f = e.fbus()[l], t = e.tbus()[l];
+                const double fr = e.vr()[f], fi = e.vi()[f], tr = e.vr()[t], ti = e.vi()[t];
                 const double ifr = y[0] * fr - y[1] * fi + y[2] * tr - y[3] * ti;
                 const double ifi = y[0] * fi + y[1] * fr + y[2] * ti + y[3] * tr;
                 const double itr = y[4] * fr - y[5] * fi + y[6] * tr - y[7] * ti;
@@ -641,210 +656,217 @@ __device__ bool loadflow(Env<TPE>& e, const PpnDevCase& c, const PpnDevCfg& cfg,
                 pf = (fr * ifr + fi * ifi) * c.base_mva; qf = (fi * ifr - fr * ifi) * c.base_mva;
                 pt = (tr * itr + ti * iti) * c.base_mva; qt = (ti * itr - tr * iti) * c.base_mva;
             }
-            e.pf[l] = pf; e.qf[l] = qf; e.pt[l] = pt; e.qt[l] = qt;
+            e.pf()[l] = pf; e.qf()[l] = qf; e.pt()[l] = pt; e.qt()[l] = qt;
         }
-        env_sync<TPE>();
+        env_sync<TPE>(mask);
         for (int b = tid; b < NB; b += TPE) {
-            if (e.btype[b] == PPN_BT_ISOLATED) continue;
-            e.vm[b] = hypot(e.vr[b], e.vi[b]);
-            e.va[b] = atan2(e.vi[b], e.vr[b]) * (180.0 / PPN_PI);
+            if (e.btype()[b] == PPN_BT_ISOLATED) continue;
+            e.vm()[b] = hypot(e.vr()[b], e.vi()[b]);
+            e.va()[b] = atan2(e.vi()[b], e.vr()[b]) * (180.0 / PPN_PI);
         }
     }
     // runpf tail: out-of-service generators report Pg = Qg = 0
     for (int g = tid; g < e.G; g += TPE)
-        if (!(e.gstat[g] > 0 && e.btype[e.gbus[g]] != PPN_BT_ISOLATED)) { e.gpg[g] = 0.0; e.gqg[g] = 0.0; }
-    env_sync<TPE>();
+        if (!(e.gstat()[g] > 0 && e.btype()[e.gbus()[g]] != PPN_BT_ISOLATED)) { e.gpg()[g] = 0.0; e.gqg()[g] = 0.0; }
+    env_sync<TPE>(mask);
     // grid.py:103-110, 263: NaN or > 1e10 in bus Vm/Va, branch flows, bus Pd
     bool bad = false;
     for (int b = tid; b < NB; b += TPE) {
-        const double a = e.vm[b], d = e.va[b];
+        const double a = e.vm()[b], d = e.va()[b];
         bad |= (a != a) || (d != d) || a > 1e10 || d > 1e10;
     }
     for (int l = tid; l < e.N; l += TPE) {
-        const double a = e.pf[l], b2 = e.qf[l], c2 = e.pt[l], d = e.qt[l];
+        const double a = e.pf()[l], b2 = e.qf()[l], c2 = e.pt()[l], d = e.qt()[l];
         bad |= (a != a) || (b2 != b2) || (c2 != c2) || (d != d) || a > 1e10 || b2 > 1e10 || c2 > 1e10 || d > 1e10;
     }
-    for (int l = tid; l < e.L; l += TPE) { const double a = e.lpd[l]; bad |= (a != a) || a > 1e10; }
-    const bool any_bad = env_any<TPE>(bad);
+    for (int l = tid; l < e.L; l += TPE) { const double a = e.lpd()[l]; bad |= (a != a) || a > 1e10; }
+    const bool any_bad = env_any<TPE>(bad, mask);
     return !success || any_bad;
 }
 
 // grid.py:112-138, 29-36
-template <int TPE> __device__ void flows_ampere(Env<TPE>& e, const PpnDevCase& c) {
+template <int TPE, class D>
+__device__ __forceinline__ void flows_ampere(Env<TPE, D>& e, const PpnDevCase& c) {
     for (int l = e.tid; l < e.N; l += TPE) {
         double a = 0.0;
-        if (e.status[l]) {
-            const int f = e.fbus[l];
-            const double p = e.pf[l], q = e.qf[l];
-            a = 1000. * sqrt(p * p + q * q) / (PPN_SQRT3 * (e.vm[f] * c.bus_basekv[f]));
+        if (e.status()[l]) {
+            const int f = e.fbus()[l];
+            const double p = e.pf()[l], q = e.qf()[l];
+            a = 1000. * sqrt(p * p + q * q) / (PPN_SQRT3 * (e.vm()[f] * c.bus_basekv[f]));
         }
-        e.amp[l] = a;
+        e.amp()[l] = a;
     }
-    env_sync<TPE>();
+    env_sync<TPE>(e.mask);
 }
 
 // game.py:503-589.  Returns true on DivergingLoadflowException.
-template <int TPE, int MAXR>
-__device__ bool cascade(Env<TPE>& e, const PpnDevCase& c, const PpnDevCfg& cfg, const PpnStepArgs& args, int slot,
+template <int TPE, int MAXR, class D>
+__device__ __forceinline__ bool cascade(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevCfg& cfg, const PpnStepArgs& args, int slot,
                         int& n_lf, int& n_it, int& depth_out) {
     int depth = 0;
-    for (int l = e.tid; l < e.N; l += TPE) e.over[l] = 0;
+    for (int l = e.tid; l < e.N; l += TPE) e.over()[l] = 0;
     while (true) {
         int it;
         n_lf++;
-        const bool div = loadflow<TPE, MAXR>(e, c, cfg, args, slot, it);
+        const bool div = loadflow<TPE, MAXR, D>(e, c, cfg, args, slot, it);
         n_it += it;
         if (div) { depth_out = depth; return true; }
         flows_ampere(e, c);
         bool any_over = false, any_trip = false;
         for (int l = e.tid; l < e.N; l += TPE) {
-            const bool over = e.amp[l] > c.thermal[l];
-            e.over[l] = over ? 1 : 0;
+            const bool over = e.amp()[l] > c.thermal[l];
+            e.over()[l] = over ? 1 : 0;
             any_over |= over;
         }
-        if (!env_any<TPE>(any_over)) break;
+        if (!env_any<TPE>(any_over, e.mask)) break;
         for (int l = e.tid; l < e.N; l += TPE) {
-            const double a = e.amp[l], lim = c.thermal[l];
+            const double a = e.amp()[l], lim = c.thermal[l];
             if (a > cfg.hard_coef * lim) {
-                e.status[l] = 0; e.recon[l] = cfg.n_hard_broken; any_trip = true; e.over[l] = 0;
-            } else if (e.over[l] && (double)e.soft[l] >= cfg.n_soft_consec) {
-                e.status[l] = 0; e.recon[l] = cfg.n_soft_broken; any_trip = true; e.over[l] = 0;
+                e.status()[l] = 0; e.recon()[l] = cfg.n_hard_broken; any_trip = true; e.over()[l] = 0;
+            } else if (e.over()[l] && (double)e.soft()[l] >= cfg.n_soft_consec) {
+                e.status()[l] = 0; e.recon()[l] = cfg.n_soft_broken; any_trip = true; e.over()[l] = 0;
             }
         }
         depth++;
-        if (!env_any<TPE>(any_trip)) break;
-        env_sync<TPE>();
+        if (!env_any<TPE>(any_trip, e.mask)) break;
+        env_sync<TPE>(e.mask);
     }
-    env_sync<TPE>();
-    for (int l = e.tid; l < e.N; l += TPE) e.soft[l] = e.over[l] ? e.soft[l] + 1 : 0;
-    env_sync<TPE>();
+    env_sync<TPE>(e.mask);
+    for (int l = e.tid; l < e.N; l += TPE) e.soft()[l] = e.over()[l] ? e.soft()[l] + 1 : 0;
+    env_sync<TPE>(e.mask);
     depth_out = depth;
     return false;
 }
 
 // reset_grid (game.py:782-797)
-template <int TPE> __device__ void reset_grid(Env<TPE>& e, const PpnDevCase& c) {
+template <int TPE, class D>
+__device__ __forceinline__ void reset_grid(Env<TPE, D>& e, const PpnDevCase& c) {
     for (int i = e.tid; i < e.N; i += TPE) {
-        e.recon[i] = 0; e.lreact[i] = 0;
-        e.onode[i] = 0; e.enode[i] = 0;
-        e.status[i] = c.line_status0[i];
+        e.recon()[i] = 0; e.lreact()[i] = 0;
+        e.onode()[i] = 0; e.enode()[i] = 0;
+        e.status()[i] = c.line_status0[i];
     }
-    for (int i = e.tid; i < e.S; i += TPE) e.nreact[i] = 0;
-    for (int i = e.tid; i < e.G; i += TPE) { e.gnode[i] = 0; e.gstat[i] = 1; }
-    for (int i = e.tid; i < e.L; i += TPE) e.lnode[i] = 0;
-    for (int b = e.tid; b < e.NB; b += TPE) { e.vm[b] = c.bus_vm0[b]; e.va[b] = c.bus_va0[b]; }
-    env_sync<TPE>();
+    for (int i = e.tid; i < e.S; i += TPE) e.nreact()[i] = 0;
+    for (int i = e.tid; i < e.G; i += TPE) { e.gnode()[i] = 0; e.gstat()[i] = 1; }
+    for (int i = e.tid; i < e.L; i += TPE) e.lnode()[i] = 0;
+    for (int b = e.tid; b < e.NB; b += TPE) { e.vm()[b] = c.bus_vm0[b]; e.va()[b] = c.bus_va0[b]; }
+    env_sync<TPE>(e.mask);
 }
 
 // Dynamic prefix of Observation.as_array (environment.py:451-466, 511-517), 7L+7G+13N+S+6 values.
-template <int TPE>
-__device__ void write_observation(Env<TPE>& e, const PpnDevCase& c, const PpnDevChronics& ch, double* out) {
+template <int TPE, class D>
+__device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevChronics& ch, double* out) {
     const int G = e.G, L = e.L, N = e.N, S = e.S, tid = e.tid;
     compute_isolated(e);
-    const float* row = chronic_row(ch, e.cursor[0], max(e.cursor[1], 0));   // maintenance horizon, date
-    const float* prow = chronic_row(ch, e.misc[6], e.misc[7]);               // planned injections
+    const float* row = chronic_row(ch, e.cursor()[0], max(e.cursor()[1], 0));   // maintenance horizon, date
+    const float* prow = chronic_row(ch, e.misc()[6], e.misc()[7]);               // planned injections
     double* o = out;
     for (int l = tid; l < L; l += TPE) {
-        o[l] = e.lpd[l];
-        o[L + l] = e.mark[e.lbus[l]] ? 1.0 : 0.0;
+        o[l] = e.lpd()[l];
+        o[L + l] = e.mark()[e.lbus()[l]] ? 1.0 : 0.0;
         o[2 * L + l] = (double)prow[ch.o_lpp + l];
-        o[3 * L + l] = (double)e.lnode[l];
+        o[3 * L + l] = (double)e.lnode()[l];
     }
     o += 4 * L;
     for (int g = tid; g < G; g += TPE) {
-        o[g] = e.gpg[g];
-        o[G + g] = e.mark[e.gbus[g]] ? 1.0 : 0.0;
+        o[g] = e.gpg()[g];
+        o[G + g] = e.mark()[e.gbus()[g]] ? 1.0 : 0.0;
         o[2 * G + g] = (double)prow[ch.o_ppp + g];
-        o[3 * G + g] = (double)e.gnode[g];
+        o[3 * G + g] = (double)e.gnode()[g];
     }
     o += 4 * G;
     const int* pm = reinterpret_cast<const int*>(row + ch.o_pm);
     for (int l = tid; l < N; l += TPE) {
-        o[l] = (double)e.onode[l];
-        o[N + l] = (double)e.enode[l];
-        o[2 * N + l] = e.amp[l];
-        o[3 * N + l] = (double)e.status[l];
-        o[4 * N + l] = (double)e.recon[l];
-        o[5 * N + l] = (double)e.lreact[l];
+        o[l] = (double)e.onode()[l];
+        o[N + l] = (double)e.enode()[l];
+        o[2 * N + l] = e.amp()[l];
+        o[3 * N + l] = (double)e.status()[l];
+        o[4 * N + l] = (double)e.recon()[l];
+        o[5 * N + l] = (double)e.lreact()[l];
         o[6 * N + S + l] = (double)pm[l];
     }
-    for (int s = tid; s < S; s += TPE) o[6 * N + s] = (double)e.nreact[s];
+    for (int s = tid; s < S; s += TPE) o[6 * N + s] = (double)e.nreact()[s];
     o += 7 * N + S;
     const int* dt = reinterpret_cast<const int*>(row + ch.o_dt);
     if (tid < 6) o[tid] = (double)dt[tid];
     o += 6;
     for (int l = tid; l < L; l += TPE) {
-        o[l] = e.lqd[l];
-        o[L + l] = e.vm[e.lbus[l]];
+        o[l] = e.lqd()[l];
+        o[L + l] = e.vm()[e.lbus()[l]];
         o[2 * L + 2 * G + 6 * N + l] = (double)prow[ch.o_lqp + l];
     }
     o += 2 * L;
     for (int g = tid; g < G; g += TPE) {
-        o[g] = e.gqg[g];
-        o[G + g] = e.gvg[g];
+        o[g] = e.gqg()[g];
+        o[G + g] = e.gvg()[g];
         const float pv = prow[ch.o_pvp + g];
-        o[2 * G + 6 * N + L + g] = (double)(pv <= 0.f ? 0.f : pv) / e.gkv[g];
+        o[2 * G + 6 * N + L + g] = (double)(pv <= 0.f ? 0.f : pv) / e.gkv()[g];
     }
     o += 2 * G;
     for (int l = tid; l < N; l += TPE) {
-        o[l] = e.pf[l];
-        o[N + l] = e.qf[l];
-        o[2 * N + l] = e.vm[e.fbus[l]];
-        o[3 * N + l] = e.pt[l];
-        o[4 * N + l] = e.qt[l];
-        o[5 * N + l] = e.vm[e.tbus[l]];
+        o[l] = e.pf()[l];
+        o[N + l] = e.qf()[l];
+        o[2 * N + l] = e.vm()[e.fbus()[l]];
+        o[3 * N + l] = e.pt()[l];
+        o[4 * N + l] = e.qt()[l];
+        o[5 * N + l] = e.vm()[e.tbus()[l]];
     }
 }
 
 // ------------------------------------------------------------------------------------------------------ the kernel
-template <int TPE, int MAXR>
-__global__ void __launch_bounds__(TPE == 32 ? 128 : TPE)
+template <int TPE, int MAXR, class D>
+__global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE)
 ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, PpnStepArgs args, int env_smem_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int envs_per_block = TPE == 32 ? (blockDim.x >> 5) : 1;
-    const int local = TPE == 32 ? (threadIdx.x >> 5) : 0;
+    const int envs_per_block = TPE <= 32 ? (blockDim.x / TPE) : 1;
+    const int local = TPE <= 32 ? (threadIdx.x / TPE) : 0;
     const int slot = blockIdx.x * envs_per_block + local;          // output row
     const int n_rows_out = args.n_envs * args.n_cand;
     if (slot >= n_rows_out) return;
     const int env = slot / args.n_cand;
-    Env<TPE> e;
-    e.tid = TPE == 32 ? (threadIdx.x & 31) : threadIdx.x;
-    env_carve(e, smem_raw + (size_t)local * env_smem_bytes, c, args.mat_cap);
+    Env<TPE, D> e;
+    e.init_dims(c);
+    e.tid = TPE <= 32 ? (threadIdx.x & (TPE - 1)) : threadIdx.x;
+    e.shift = TPE < 32 ? ((threadIdx.x & 31) & ~(TPE - 1)) : 0;
+    e.mask = TPE < 32 ? (((1u << TPE) - 1u) << e.shift) : PPN_FULL;
+    e.base = smem_raw + (size_t)local * env_smem_bytes;
+    e.fixed_bytes = env_smem_bytes - 8 * args.mat_cap;
     const int tid = e.tid, S = e.S, G = e.G, L = e.L, N = e.N, NB = e.NB;
+    const unsigned mask = e.mask;
     const int mode = args.mode;
     const bool is_sim = mode == PPN_MODE_SIMULATE;
     if (mode == PPN_MODE_GAME_OVER && args.mask && !args.mask[env]) return;
 
     // ---- state in
     if (mode == PPN_MODE_INIT) {
-        for (int b = tid; b < NB; b += TPE) { e.vm[b] = c.bus_vm0[b]; e.va[b] = c.bus_va0[b]; }
-        for (int l = tid; l < L; l += TPE) { e.lpd[l] = c.load_pd0[l]; e.lqd[l] = c.load_qd0[l]; e.lnode[l] = 0; }
+        for (int b = tid; b < NB; b += TPE) { e.vm()[b] = c.bus_vm0[b]; e.va()[b] = c.bus_va0[b]; }
+        for (int l = tid; l < L; l += TPE) { e.lpd()[l] = c.load_pd0[l]; e.lqd()[l] = c.load_qd0[l]; e.lnode()[l] = 0; }
         for (int g = tid; g < G; g += TPE) {
-            e.gpg[g] = c.gen_pg0[g]; e.gqg[g] = c.gen_qg0[g]; e.gvg[g] = c.gen_vg0[g]; e.gnode[g] = 0; e.gstat[g] = 1;
+            e.gpg()[g] = c.gen_pg0[g]; e.gqg()[g] = c.gen_qg0[g]; e.gvg()[g] = c.gen_vg0[g]; e.gnode()[g] = 0; e.gstat()[g] = 1;
         }
         for (int l = tid; l < N; l += TPE) {
-            e.onode[l] = 0; e.enode[l] = 0; e.status[l] = c.line_status0[l];
-            e.recon[l] = 0; e.lreact[l] = 0; e.soft[l] = 0;
+            e.onode()[l] = 0; e.enode()[l] = 0; e.status()[l] = c.line_status0[l];
+            e.recon()[l] = 0; e.lreact()[l] = 0; e.soft()[l] = 0;
         }
-        for (int s = tid; s < S; s += TPE) e.nreact[s] = 0;
+        for (int s = tid; s < S; s += TPE) e.nreact()[s] = 0;
         if (tid == 0) {
             const int start = args.init_chronic ? args.init_chronic[env] : 0;
             const int row0 = args.init_row0 ? args.init_row0[env] : 0;
-            e.cursor[2] = start; e.cursor[3] = 0;
-            e.cursor[0] = take_next_chronic(e.cursor, cfg, ch.n_chronics, env);
-            e.cursor[1] = row0 - 1;   // -1: no row played yet
+            e.cursor()[2] = start; e.cursor()[3] = 0;
+            e.cursor()[0] = take_next_chronic(e.cursor(), cfg, ch.n_chronics, env);
+            e.cursor()[1] = row0 - 1;   // -1: no row played yet
         }
     } else {
         const double* sr = st.real + (size_t)env * st.rw;
-        for (int b = tid; b < 2 * NB; b += TPE) e.vm[b] = sr[b];            // vm | va are adjacent
-        for (int l = tid; l < 2 * L; l += TPE) e.lpd[l] = sr[2 * NB + l];   // lpd | lqd adjacent
-        for (int g = tid; g < 3 * G; g += TPE) e.gpg[g] = sr[2 * NB + 2 * L + g];  // gpg | gqg | gvg adjacent
+        for (int b = tid; b < 2 * NB; b += TPE) e.vm()[b] = sr[b];            // vm | va are adjacent
+        for (int l = tid; l < 2 * L; l += TPE) e.lpd()[l] = sr[2 * NB + l];   // lpd | lqd adjacent
+        for (int g = tid; g < 3 * G; g += TPE) e.gpg()[g] = sr[2 * NB + 2 * L + g];  // gpg | gqg | gvg adjacent
         const uint8_t* tr = st.topo + (size_t)env * st.tw;
-        for (int i = tid; i < 2 * G + L + 3 * N; i += TPE) e.gnode[i] = tr[i];
+        for (int i = tid; i < 2 * G + L + 3 * N; i += TPE) e.gnode()[i] = tr[i];
         const int32_t* cr = st.cnt + (size_t)env * st.cw;
-        for (int i = tid; i < 3 * N + S + 4; i += TPE) e.recon[i] = cr[i];
+        for (int i = tid; i < 3 * N + S + 4; i += TPE) e.recon()[i] = cr[i];
     }
-    env_sync<TPE>();
+    env_sync<TPE>(mask);
 
     int flag = 0;
     bool done = false, illegal = false, too_much = false;
@@ -854,87 +876,111 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
     if (mode == PPN_MODE_STEP || mode == PPN_MODE_SIMULATE) {
         // ---- action: legality (game.py:650-753), correction (game.py:809-854), application (game.py:591-648)
         const int NT = G + L + 2 * N;  // node-switch part
+        bool any_set = false;
         if (args.act) {
-            const uint8_t* a = args.act + (size_t)slot * c.A;
-            for (int i = tid; i < c.A; i += TPE) e.act[i] = a[i];
-        } else {
-            for (int i = tid; i < c.A; i += TPE) e.act[i] = 0;
+            const uint8_t* a = args.act + (size_t)slot * e.A;
+            for (int i = tid; i < e.A; i += TPE) { const uint8_t v = a[i]; e.act()[i] = v; any_set |= v != 0; }
         }
-        for (int s = tid; s < S; s += TPE) e.subch[s] = 0;
-        env_sync<TPE>();
-        for (int i = tid; i < NT; i += TPE)
-            if (e.act[i]) e.subch[c.elem_sub[i]] = 1;
-        env_sync<TPE>();
-        int ns = 0, nl = 0;
-        for (int s = tid; s < S; s += TPE) ns += e.subch[s];
-        for (int l = tid; l < N; l += TPE) nl += (e.act[NT + l] == 1);
-        ns = env_sum_int<TPE>(ns, e.redi, tid);
-        nl = env_sum_int<TPE>(nl, e.redi + TPE / 32, tid);
-        too_much = ns > cfg.max_sub || nl > cfg.max_lines || ns + nl > cfg.max_total;
-        for (int i = tid; i < 1 + 2 * N + S; i += TPE) e.ill[i] = 0;
-        env_sync<TPE>();
-        if (too_much) {
-            illegal = true;
-            if (tid == 0) e.ill[0] = 1;
-            for (int i = tid; i < c.A; i += TPE) e.act[i] = 0;
-            for (int s = tid; s < S; s += TPE) e.subch[s] = 0;
-        } else {
-            int cnt = 0;
-            for (int l = tid; l < N; l += TPE) {
-                const bool sw = e.act[NT + l] == 1;
-                const bool r1 = sw && e.recon[l] > 0, r2 = sw && e.lreact[l] > 0;
-                e.ill[1 + l] = r1; e.ill[1 + N + l] = r2;
-                cnt += r1 + r2;
-                if (r1 || r2) e.act[NT + l] = 0;
-            }
-            for (int s = tid; s < S; s += TPE) {
-                const bool r3 = e.subch[s] && e.nreact[s] > 0;
-                e.ill[1 + 2 * N + s] = r3;
-                cnt += r3;
-            }
-            n_ill = env_sum_int<TPE>(cnt, e.redi, tid);
-            illegal = n_ill > 0;
-            env_sync<TPE>();
+        any_set = env_any<TPE>(any_set, mask);
+        if (any_set) {   // a do-nothing action changes nothing and is always legal
+            for (int s = tid; s < S; s += TPE) e.subch()[s] = 0;
+            env_sync<TPE>(mask);
             for (int i = tid; i < NT; i += TPE)
-                if (e.ill[1 + 2 * N + c.elem_sub[i]]) e.act[i] = 0;
+                if (e.act()[i]) e.subch()[c.elem_sub[i]] = 1;
+            env_sync<TPE>(mask);
+            int ns = 0, nl = 0;
+            for (int s = tid; s < S; s += TPE) ns += e.subch()[s];
+            for (int l = tid; l < N; l += TPE) nl += (e.act()[NT + l] == 1);
+            ns = env_sum_int<TPE>(ns, e.redi(), tid, mask);
+            nl = env_sum_int<TPE>(nl, e.redi() + (TPE + 31) / 32, tid, mask);
+            too_much = ns > cfg.max_sub || nl > cfg.max_lines || ns + nl > cfg.max_total;
+            for (int i = tid; i < 1 + 2 * N + S; i += TPE) e.ill()[i] = 0;
+            env_sync<TPE>(mask);
+            if (too_much) {
+                illegal = true;
+                if (tid == 0) e.ill()[0] = 1;
+                for (int i = tid; i < e.A; i += TPE) e.act()[i] = 0;
+                for (int s = tid; s < S; s += TPE) e.subch()[s] = 0;
+            } else {
+                int cnt = 0;
+                for (int l = tid; l < N; l += TPE) {
+                    const bool sw = e.act()[NT + l] == 1;
+                    const bool r1 = sw && e.recon()[l] > 0, r2 = sw && e.lreact()[l] > 0;
+                    e.ill()[1 + l] = r1; e.ill()[1 + N + l] = r2;
+                    cnt += r1 + r2;
+                    if (r1 || r2) e.act()[NT + l] = 0;
+                }
+                for (int s = tid; s < S; s += TPE) {
+                    const bool r3 = e.subch()[s] && e.nreact()[s] > 0;
+                    e.ill()[1 + 2 * N + s] = r3;
+                    cnt += r3;
+                }
+                n_ill = env_sum_int<TPE>(cnt, e.redi(), tid, mask);
+                illegal = n_ill > 0;
+                env_sync<TPE>(mask);
+                for (int i = tid; i < NT; i += TPE)
+                    if (e.ill()[1 + 2 * N + c.elem_sub[i]]) e.act()[i] = 0;
+                for (int s = tid; s < S; s += TPE)
+                    if (e.ill()[1 + 2 * N + s]) e.subch()[s] = 0;
+            }
+            env_sync<TPE>(mask);
+            // apply: new = where(bit, 1 - cur, cur); loads follow their node bit (the Pd/Qd swap of grid.py:405-421)
+            int cn = 0, cl = 0;
+            for (int i = tid; i < NT; i += TPE) {
+                if (e.act()[i]) { e.gnode()[i] ^= 1; cn += e.act()[i]; }   // gnode|lnode|onode|enode are adjacent
+            }
+            for (int l = tid; l < N; l += TPE) {
+                const int a = e.act()[NT + l];
+                if (a) { e.status()[l] ^= 1; cl += a; }
+                if (a == 1) e.lreact()[l] = cfg.n_line_react;
+            }
             for (int s = tid; s < S; s += TPE)
-                if (e.ill[1 + 2 * N + s]) e.subch[s] = 0;
+                if (e.subch()[s]) e.nreact()[s] = cfg.n_node_react;
+            cost_nodes = env_sum_int<TPE>(cn, e.redi(), tid, mask);
+            cost_lines = env_sum_int<TPE>(cl, e.redi() + (TPE + 31) / 32, tid, mask);
+            env_sync<TPE>(mask);
+        } else if (args.illegal) {
+            for (int i = tid; i < 1 + 2 * N + S; i += TPE) e.ill()[i] = 0;
+            env_sync<TPE>(mask);
         }
-        env_sync<TPE>();
-        // apply: new = where(bit, 1 - cur, cur); loads follow their node bit (the Pd/Qd swap of grid.py:405-421)
-        int cn = 0, cl = 0;
-        for (int i = tid; i < NT; i += TPE) {
-            if (e.act[i]) { e.gnode[i] ^= 1; cn += e.act[i]; }   // gnode|lnode|onode|enode are adjacent
-        }
-        for (int l = tid; l < N; l += TPE) {
-            const int a = e.act[NT + l];
-            if (a) { e.status[l] ^= 1; cl += a; }
-            if (a == 1) e.lreact[l] = cfg.n_line_react;
-        }
-        for (int s = tid; s < S; s += TPE)
-            if (e.subch[s]) e.nreact[s] = cfg.n_node_react;
-        cost_nodes = env_sum_int<TPE>(cn, e.redi, tid);
-        cost_lines = env_sum_int<TPE>(cl, e.redi + TPE / 32, tid);
-        env_sync<TPE>();
     }
 
-    bool need_reset = false;
-    if (mode != PPN_MODE_GAME_OVER) {
+    // One loop, two kinds of pass: the step itself (not for PPN_MODE_GAME_OVER), then process_game_over passes
+    // (game.py:762-780: reset, next row -- next chronic in hard mode --, cascade; again while it diverges).
+    bool reset_pass = mode == PPN_MODE_GAME_OVER;
+    int attempts = 0;
+    while (true) {
+        if (reset_pass) {
+            reset_grid(e, c);
+            if (cfg.hard_mode) {
+                if (tid == 0) {
+                    e.cursor()[0] = take_next_chronic(e.cursor(), cfg, ch.n_chronics, env);
+                    e.cursor()[1] = -2;
+                }
+                env_sync<TPE>(mask);
+            }
+            n_resets++;
+        }
         refresh_element_buses(e, c);
-        load_next_timestep(e, c, ch, cfg, is_sim, env);
-        const bool div = cascade<TPE, MAXR>(e, c, cfg, args, slot, n_lf, n_it, depth);
+        load_next_timestep(e, c, ch, cfg, is_sim && !reset_pass, env);
+        int d2 = 0;
+        const bool div = cascade<TPE, MAXR, D>(e, c, cfg, args, slot, n_lf, n_it, d2);
+        if (reset_pass) {
+            if (!div || ++attempts >= cfg.max_reset_attempts) { done = false; break; }
+            continue;
+        }
+        depth = d2;
+        int nlc = 0, npc = 0;
         if (div) {
             flag = 2; done = true;
         } else if (mode != PPN_MODE_INIT) {   // Game.__init__ (game.py:339-340) only runs the cascade
             compute_isolated(e);
-            int nlc = 0, npc = 0;
-            for (int l = tid; l < L; l += TPE) nlc += e.mark[e.lbus[l]];
-            for (int g = tid; g < G; g += TPE) npc += e.mark[e.gbus[g]];
-            nlc = env_sum_int<TPE>(nlc, e.redi, tid);
-            npc = env_sum_int<TPE>(npc, e.redi + TPE / 32, tid);
+            for (int l = tid; l < L; l += TPE) nlc += e.mark()[e.lbus()[l]];
+            for (int g = tid; g < G; g += TPE) npc += e.mark()[e.gbus()[g]];
+            nlc = env_sum_int<TPE>(nlc, e.redi(), tid, mask);
+            npc = env_sum_int<TPE>(npc, e.redi() + (TPE + 31) / 32, tid, mask);
             if (nlc > cfg.max_loads_go) { flag = 3; done = true; }
             else if (npc > cfg.max_prods_go) { flag = 4; done = true; }
-            e.misc[4] = nlc; e.misc[5] = npc;
         }
         if (flag == 0 && illegal) flag = 1;
         // ---- reward (parameters/default14/reward_signal.py:45-169)
@@ -947,13 +993,13 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
             else if (flag == 3) { r0 = -k; }
             else {
                 int dist = 0;
-                for (int i = tid; i < G + L + 2 * N; i += TPE) dist += e.gnode[i];
-                dist = env_sum_int<TPE>(dist, e.redi, tid);
+                for (int i = tid; i < G + L + 2 * N; i += TPE) dist += e.gnode()[i];
+                dist = env_sum_int<TPE>(dist, e.redi(), tid, mask);
                 double u = 0.0;
-                for (int l = tid; l < N; l += TPE) { const double x = e.amp[l] / c.thermal[l]; u += x * x; }
-                u = env_sum_double<TPE>(u, e.redd, tid);
-                r0 = -k / 5. * (double)e.misc[4];
-                r1 = -k / 10. * (double)e.misc[5];
+                for (int l = tid; l < N; l += TPE) { const double x = e.amp()[l] / c.thermal[l]; u += x * x; }
+                u = env_sum_double<TPE>(u, e.redd(), tid, mask);
+                r0 = -k / 5. * (double)nlc;
+                r1 = -k / 10. * (double)npc;
                 r2 = cost;
                 r3 = -.02 * (double)dist;
                 r4 = -1. * u;
@@ -973,33 +1019,10 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
         }
         if (args.illegal && mode != PPN_MODE_INIT) {
             uint8_t* il = args.illegal + (size_t)slot * (1 + 2 * N + S);
-            for (int i = tid; i < 1 + 2 * N + S; i += TPE) il[i] = e.ill[i];
+            for (int i = tid; i < 1 + 2 * N + S; i += TPE) il[i] = e.ill()[i];
         }
-        need_reset = done && !is_sim && (args.auto_reset || mode == PPN_MODE_INIT);
-    } else {
-        need_reset = true;
-    }
-
-    // ---- process_game_over (game.py:762-780): reset, next row (next chronic in hard mode), cascade; again if it diverges
-    if (need_reset) {
-        int attempts = 0;
-        while (true) {
-            reset_grid(e, c);
-            if (cfg.hard_mode) {
-                if (tid == 0) {
-                    e.cursor[0] = take_next_chronic(e.cursor, cfg, ch.n_chronics, env);
-                    e.cursor[1] = -2;
-                }
-                env_sync<TPE>();
-            }
-            refresh_element_buses(e, c);
-            load_next_timestep(e, c, ch, cfg, false, env);
-            n_resets++;
-            int d2;
-            const bool div = cascade<TPE, MAXR>(e, c, cfg, args, slot, n_lf, n_it, d2);
-            if (!div || ++attempts >= cfg.max_reset_attempts) break;
-        }
-        done = false;
+        if (!(done && !is_sim && (args.auto_reset || mode == PPN_MODE_INIT))) break;
+        reset_pass = true;
     }
 
     // ---- outputs
@@ -1008,15 +1031,15 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
         write_observation(e, c, ch, args.obs + (size_t)slot * args.obs_stride);
     }
     if (!is_sim) {
-        env_sync<TPE>();
+        env_sync<TPE>(mask);
         double* sr = st.real + (size_t)env * st.rw;
-        for (int b = tid; b < 2 * NB; b += TPE) sr[b] = e.vm[b];
-        for (int l = tid; l < 2 * L; l += TPE) sr[2 * NB + l] = e.lpd[l];
-        for (int g = tid; g < 3 * G; g += TPE) sr[2 * NB + 2 * L + g] = e.gpg[g];
+        for (int b = tid; b < 2 * NB; b += TPE) sr[b] = e.vm()[b];
+        for (int l = tid; l < 2 * L; l += TPE) sr[2 * NB + l] = e.lpd()[l];
+        for (int g = tid; g < 3 * G; g += TPE) sr[2 * NB + 2 * L + g] = e.gpg()[g];
         uint8_t* tr = st.topo + (size_t)env * st.tw;
-        for (int i = tid; i < 2 * G + L + 3 * N; i += TPE) tr[i] = e.gnode[i];
+        for (int i = tid; i < 2 * G + L + 3 * N; i += TPE) tr[i] = e.gnode()[i];
         int32_t* cr = st.cnt + (size_t)env * st.cw;
-        for (int i = tid; i < 3 * N + S + 4; i += TPE) cr[i] = e.recon[i];
+        for (int i = tid; i < 3 * N + S + 4; i += TPE) cr[i] = e.recon()[i];
     }
     if (args.stats && tid == 0) {
         atomicAdd(args.stats + 0, (unsigned long long)n_lf);
@@ -1027,34 +1050,47 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
     }
 }
 
+template <int TPE, int MAXR, class D>
+int launch_group(const PpnDevCase* c, const PpnDevChronics* ch, const PpnDevCfg* cfg, const PpnDevState* st,
+                 const PpnStepArgs* args, int envs_per_block, int env_smem_bytes, cudaStream_t stream) {
+    const int rows = args->n_envs * args->n_cand;
+    const int epb = TPE <= 32 ? envs_per_block : 1;
+    const int grid = (rows + epb - 1) / epb;
+    const size_t smem = (size_t)epb * env_smem_bytes;
+    auto k = ppn_step_kernel<TPE, MAXR, D>;
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    k<<<grid, TPE <= 32 ? epb * TPE : TPE, smem, stream>>>(*c, *ch, *cfg, *st, *args, env_smem_bytes);
+    return (int)cudaGetLastError();
+}
+
+typedef StaticDims<14, 5, 11, 20> Dims14;      // IEEE-14  (parameters/default14)
+typedef StaticDims<30, 6, 20, 41> Dims30;      // IEEE-30  (parameters/default30)
+typedef StaticDims<118, 54, 99, 186> Dims118;  // IEEE-118 (parameters/default118)
+
+template <class SD> bool dims_match(const PpnDevCase* c) {
+    return c->S == SD::S && c->G == SD::G && c->L == SD::L && c->N == SD::N;
+}
+
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------- launch wrapper
+// tpe: 16 (<= 16 substations), 32 (<= 32 substations) or 256 (one CTA per env, <= 128 substations).  The three IEEE
+// families run kernels specialised on their sizes; any other grid runs the size-generic instantiation.
 extern "C" int ppn_launch_step(const PpnDevCase* c, const PpnDevChronics* ch, const PpnDevCfg* cfg, const PpnDevState* st,
                                const PpnStepArgs* args, int tpe, int envs_per_block, int env_smem_bytes,
                                cudaStream_t stream) {
-    const int rows = args->n_envs * args->n_cand;
-    if (rows <= 0) return 0;
-    cudaError_t err;
-    if (tpe == 32) {
-        const int grid = (rows + envs_per_block - 1) / envs_per_block;
-        const size_t smem = (size_t)envs_per_block * env_smem_bytes;
-        auto k = ppn_step_kernel<32, 2>;
-        err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        k<<<grid, envs_per_block * 32, smem, stream>>>(*c, *ch, *cfg, *st, *args, env_smem_bytes);
-    } else if (tpe == 128) {
-        auto k = ppn_step_kernel<128, 8>;
-        err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, env_smem_bytes);
-        if (err != cudaSuccess) return (int)err;
-        k<<<rows, 128, env_smem_bytes, stream>>>(*c, *ch, *cfg, *st, *args, env_smem_bytes);
-    } else if (tpe == 256) {
-        auto k = ppn_step_kernel<256, 8>;
-        err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, env_smem_bytes);
-        if (err != cudaSuccess) return (int)err;
-        k<<<rows, 256, env_smem_bytes, stream>>>(*c, *ch, *cfg, *st, *args, env_smem_bytes);
-    } else {
-        return (int)cudaErrorInvalidValue;
+    if (args->n_envs * args->n_cand <= 0) return 0;
+    switch (tpe) {
+        case 16:
+            if (dims_match<Dims14>(c)) return launch_group<16, 2, Dims14>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+            return launch_group<16, 2, DynDims>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+        case 32:
+            if (dims_match<Dims30>(c)) return launch_group<32, 2, Dims30>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+            return launch_group<32, 2, DynDims>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+        case 256:
+            if (dims_match<Dims118>(c)) return launch_group<256, 8, Dims118>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+            return launch_group<256, 8, DynDims>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+        default: return (int)cudaErrorInvalidValue;
     }
-    return (int)cudaGetLastError();
 }

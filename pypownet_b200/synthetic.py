@@ -13,14 +13,16 @@ from pypownet_b200.chronic import Chronic
 
 
 def make_chronic(case, n_rows, seed, name=None, p_maintenance=0.019, p_hazard=0.011, p_gen_off=0.06,
-                 thermal_limits=None):
+                 thermal_limits=None, load_level=None):
     rng = np.random.default_rng(seed)
     G, L, N, S = case.n_gen, case.n_load, case.n_line, case.n_sub
     T = int(n_rows)
     t = np.arange(T + 1)                                   # one more row: `planned[t] := planned[t+1]`
     phase = rng.uniform(0, 24)
     daily = 1.0 + 0.17 * np.sin(2 * np.pi * (t - 9 + phase) / 24.) + 0.07 * np.sin(4 * np.pi * (t + phase) / 24.)
-    level = 1.2 * daily * (1 + 0.03 * rng.standard_normal(T + 1))
+    if load_level is None:                                 # mean load / case-file load in the shipped chronics
+        load_level = 1.2 if S <= 14 else (1.03 if S <= 30 else 0.9)
+    level = load_level * daily * (1 + 0.03 * rng.standard_normal(T + 1))
     base_p = case.bus_pd0[case.load_sub]
     base_q = case.bus_qd0[case.load_sub]
     loads_p = base_p[None, :] * level[:, None] * (1 + 0.05 * rng.standard_normal((T + 1, L)))
@@ -80,10 +82,10 @@ DEFAULT_CONFIG = {
 def default_config(casename, **overrides):
     cfg = dict(DEFAULT_CONFIG)
     if casename == 'case30':
-        cfg.update(max_number_prods_game_over=2, max_number_loads_game_over=0, max_number_actionned_substations=10,
-                   max_number_actionned_lines=15, max_number_actionned_total=20)
+        cfg.update(max_number_actionned_substations=10, max_number_actionned_lines=15, max_number_actionned_total=20)
     elif casename == 'case118':
-        cfg.update(max_number_prods_game_over=10, max_number_loads_game_over=0, max_number_actionned_substations=25,
-                   max_number_actionned_lines=40, max_number_actionned_total=50)
+        cfg.update(hard_overflow_coefficient=2.0, n_timesteps_hard_overflow_is_broken=4,
+                   n_timesteps_soft_overflow_is_broken=2, max_number_prods_game_over=10, max_number_loads_game_over=5,
+                   max_number_actionned_substations=25, max_number_actionned_lines=40, max_number_actionned_total=50)
     cfg.update(overrides)
     return cfg
