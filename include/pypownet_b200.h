@@ -168,8 +168,9 @@ int ppn_obs_dynamic_length(const ppn_env* env);
 int ppn_device(const ppn_env* env);
 /* number of kernel launches issued by this handle so far, and cumulative device counters:
  * out_host[0] load-flows, [1] fast-decoupled iterations, [2] env steps, [3] game-over resets, [4] max cascade depth,
- * [5] kernel launches, [6] shared-memory bytes per env, [7] threads per env */
-int ppn_get_counters(ppn_env* env, int64_t* out_host /* [8] */);
+ * [5] kernel launches, [6] shared-memory bytes per env, [7] threads per env, [8] most load-flows and [9] most
+ * fast-decoupled iterations spent by one env in one call since the previous ppn_get_counters */
+int ppn_get_counters(ppn_env* env, int64_t* out_host /* [10] */);
 const char* ppn_last_error(const ppn_env* env);
 const char* ppn_build_info(void);
 void ppn_destroy(ppn_env* env);

@@ -205,7 +205,7 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
 
     // ---- threads per env and shared-memory plan
     int tpe = cfg->threads_per_env;
-    if (tpe == 0) tpe = (NB <= 32) ? 16 : ((NB <= 64) ? 32 : 256);
+    if (tpe == 0) tpe = (NB <= 64) ? 32 : 256;   // measured on B200: a full warp per env beats two envs per warp
     if (tpe != 16 && tpe != 32 && tpe != 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env must be 0, 16, 32 or 256"); }
     if ((tpe == 16 && NB > 32) || (tpe == 32 && NB > 64) || NB > 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env too small for this grid (16: <= 16 substations, 32: <= 32, 256: <= 128)"); }
     env->tpe = tpe;
@@ -218,7 +218,7 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     int want = n1 * (n1 | 1) + n2 * (n2 | 1);
     const int worst = 2 * (NB - 1) * ((NB - 1) | 1);
     if (want > worst) want = worst;
-    env->envs_per_block = tpe == 16 ? 2 : 1;                 // one warp per CTA for the sub-warp / warp kernels
+    env->envs_per_block = tpe == 16 ? 4 : 2;                 // 64-thread CTAs for the sub-warp / warp kernels
     int cap_bytes = max_smem / env->envs_per_block - fixed - 64;
     if (cap_bytes < 0) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "grid too large for the shared-memory plan"); }
     int cap = cap_bytes / 8;
@@ -561,5 +561,9 @@ extern "C" int ppn_get_counters(ppn_env* env, int64_t* out_host) {
     out_host[5] = env->launches;
     out_host[6] = env->env_smem_bytes;
     out_host[7] = env->tpe;
+    out_host[8] = (int64_t)h[5];
+    out_host[9] = (int64_t)h[6];
+    // the two maxima restart after every read
+    CK(cudaMemset(env->stats + 5, 0, 2 * sizeof(unsigned long long)));
     return PPN_OK;
 }

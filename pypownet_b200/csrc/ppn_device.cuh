@@ -115,10 +115,11 @@ static inline __host__ __device__ int ppn_env_smem_fixed_bytes(int S, int G, int
     const int NB = 2 * S;
     const int A = G + L + 3 * N;
     const int nw = (tpe + 31) / 32;
-    int dbl = 12 * NB + 5 * N + 2 * L + 4 * G + nw * 2;   // per-bus, per-line, per-load, per-gen arrays + reduction scratch
+    const int un = 4 * NB > 5 * N ? 4 * NB : 5 * N;     // FD work arrays share storage with the branch results
+    int dbl = 8 * NB + un + 4 * N + 2 * L + 4 * G + nw * 2;
     int i32 = 3 * N + S + 4 + nw * 2 + 8;
     int i16 = 2 * N + 4 * NB + G + L + 4 * N;
-    int u8 = (2 * G + L + 3 * N) + 2 * NB + N + A + S + (1 + 2 * N + S);
+    int u8 = (2 * G + L + 3 * N) + 2 * NB + N + A + S + (1 + 2 * N + S) + NB;
     int bytes = dbl * 8 + i32 * 4 + ((i16 * 2 + 3) & ~3) + ((u8 + 7) & ~7);
     return (bytes + 15) & ~15;
 }

@@ -104,18 +104,23 @@ template <int TPE, class D> struct Env : D {
     int fixed_bytes;
     static constexpr int NW = (TPE + 31) / 32;
 #define PPN_DBL(name, expr) __device__ __forceinline__ double* name() const { return reinterpret_cast<double*>(base) + (expr); }
+    // U: the fast-decoupled work arrays (P, Q mismatches, Ybus diagonal) share their storage with the branch results
+    // (flows, amperes), which are only written once the iteration is over.
+    __device__ __forceinline__ int n_union() const { return 4 * this->NB > 5 * this->N ? 4 * this->NB : 5 * this->N; }
     PPN_DBL(vm, 0) PPN_DBL(va, this->NB) PPN_DBL(vr, 2 * this->NB) PPN_DBL(vi, 3 * this->NB)
-    PPN_DBL(pin, 4 * this->NB) PPN_DBL(qin, 5 * this->NB) PPN_DBL(P, 6 * this->NB) PPN_DBL(Q, 7 * this->NB)
-    PPN_DBL(ydr, 8 * this->NB) PPN_DBL(ydi, 9 * this->NB) PPN_DBL(cs, 10 * this->NB) PPN_DBL(sn, 11 * this->NB)
-    PPN_DBL(pf, 12 * this->NB) PPN_DBL(qf, 12 * this->NB + this->N) PPN_DBL(pt, 12 * this->NB + 2 * this->N)
-    PPN_DBL(qt, 12 * this->NB + 3 * this->N) PPN_DBL(amp, 12 * this->NB + 4 * this->N)
-    PPN_DBL(lpd, 12 * this->NB + 5 * this->N) PPN_DBL(lqd, 12 * this->NB + 5 * this->N + this->L)
-    PPN_DBL(gpg, 12 * this->NB + 5 * this->N + 2 * this->L) PPN_DBL(gqg, 12 * this->NB + 5 * this->N + 2 * this->L + this->G)
-    PPN_DBL(gvg, 12 * this->NB + 5 * this->N + 2 * this->L + 2 * this->G)
-    PPN_DBL(gkv, 12 * this->NB + 5 * this->N + 2 * this->L + 3 * this->G)
-    PPN_DBL(redd, 12 * this->NB + 5 * this->N + 2 * this->L + 4 * this->G)
+    PPN_DBL(pin, 4 * this->NB) PPN_DBL(qin, 5 * this->NB) PPN_DBL(cs, 6 * this->NB) PPN_DBL(sn, 7 * this->NB)
+    PPN_DBL(P, 8 * this->NB) PPN_DBL(Q, 9 * this->NB) PPN_DBL(ydr, 10 * this->NB) PPN_DBL(ydi, 11 * this->NB)
+    PPN_DBL(pf, 8 * this->NB) PPN_DBL(qf, 8 * this->NB + this->N) PPN_DBL(pt, 8 * this->NB + 2 * this->N)
+    PPN_DBL(qt, 8 * this->NB + 3 * this->N) PPN_DBL(amp, 8 * this->NB + 4 * this->N)
+    PPN_DBL(eyr, 8 * this->NB + n_union()) PPN_DBL(eyi, 8 * this->NB + n_union() + 2 * this->N)
+    PPN_DBL(lpd, 8 * this->NB + n_union() + 4 * this->N) PPN_DBL(lqd, 8 * this->NB + n_union() + 4 * this->N + this->L)
+    PPN_DBL(gpg, 8 * this->NB + n_union() + 4 * this->N + 2 * this->L)
+    PPN_DBL(gqg, 8 * this->NB + n_union() + 4 * this->N + 2 * this->L + this->G)
+    PPN_DBL(gvg, 8 * this->NB + n_union() + 4 * this->N + 2 * this->L + 2 * this->G)
+    PPN_DBL(gkv, 8 * this->NB + n_union() + 4 * this->N + 2 * this->L + 3 * this->G)
+    PPN_DBL(redd, 8 * this->NB + n_union() + 4 * this->N + 2 * this->L + 4 * this->G)
 #undef PPN_DBL
-    __device__ __forceinline__ int n_dbl() const { return 12 * this->NB + 5 * this->N + 2 * this->L + 4 * this->G + 2 * NW; }
+    __device__ __forceinline__ int n_dbl() const { return 8 * this->NB + n_union() + 4 * this->N + 2 * this->L + 4 * this->G + 2 * NW; }
 #define PPN_I32(name, expr) __device__ __forceinline__ int* name() const { return reinterpret_cast<int*>(base + 8 * n_dbl()) + (expr); }
     PPN_I32(recon, 0) PPN_I32(lreact, this->N) PPN_I32(soft, 2 * this->N) PPN_I32(nreact, 3 * this->N)
     PPN_I32(cursor, 3 * this->N + this->S) PPN_I32(redi, 3 * this->N + this->S + 4) PPN_I32(misc, 3 * this->N + this->S + 4 + 2 * NW)
@@ -125,7 +130,7 @@ template <int TPE, class D> struct Env : D {
     PPN_I16(fbus, 0) PPN_I16(tbus, this->N) PPN_I16(idxp, 2 * this->N) PPN_I16(idxq, 2 * this->N + this->NB)
     PPN_I16(busp, 2 * this->N + 2 * this->NB) PPN_I16(busq, 2 * this->N + 3 * this->NB)
     PPN_I16(gbus, 2 * this->N + 4 * this->NB) PPN_I16(lbus, 2 * this->N + 4 * this->NB + this->G)
-    PPN_I16(ebus, 2 * this->N + 4 * this->NB + this->G + this->L) PPN_I16(eoth, 4 * this->N + 4 * this->NB + this->G + this->L)
+    PPN_I16(eline, 2 * this->N + 4 * this->NB + this->G + this->L) PPN_I16(eoth, 4 * this->N + 4 * this->NB + this->G + this->L)
 #undef PPN_I16
     __device__ __forceinline__ int n_i16() const { return 6 * this->N + 4 * this->NB + this->G + this->L; }
 #define PPN_U8(name, expr) __device__ __forceinline__ uint8_t* name() const { return base + 8 * n_dbl() + 4 * n_i32() + ((2 * n_i16() + 3) & ~3) + (expr); }
@@ -136,6 +141,7 @@ template <int TPE, class D> struct Env : D {
     PPN_U8(over, 2 * this->G + this->L + 3 * this->N + 2 * this->NB) PPN_U8(act, 2 * this->G + this->L + 4 * this->N + 2 * this->NB)
     PPN_U8(subch, 2 * this->G + this->L + 4 * this->N + 2 * this->NB + this->A)
     PPN_U8(ill, 2 * this->G + this->L + 4 * this->N + 2 * this->NB + this->A + this->S)
+    PPN_U8(deg, 2 * this->G + this->L + 6 * this->N + 2 * this->NB + this->A + 2 * this->S + 1)
 #undef PPN_U8
     __device__ __forceinline__ double* mat() const { return reinterpret_cast<double*>(base + fixed_bytes); }
 };
@@ -165,7 +171,15 @@ template <int TPE, int MAXR> __device__ void gj_invert(double* a, int n, int ld,
                 const double ci = cm[r];
                 double* ai = a + i * ld;
                 const double* ak = a + k * ld;
-                for (int j = w; j < n; j += W) ai[j] = fma(-ci, ak[j], ai[j]);   // column k fixed just below
+                // column k is fixed just below; four elements per trip, loads first (ai and ak never overlap: i != k)
+                int j = w;
+                for (; j + 3 * W < n; j += 4 * W) {
+                    const double k0 = ak[j], k1 = ak[j + W], k2 = ak[j + 2 * W], k3 = ak[j + 3 * W];
+                    const double x0 = ai[j], x1 = ai[j + W], x2 = ai[j + 2 * W], x3 = ai[j + 3 * W];
+                    ai[j] = fma(-ci, k0, x0); ai[j + W] = fma(-ci, k1, x1);
+                    ai[j + 2 * W] = fma(-ci, k2, x2); ai[j + 3 * W] = fma(-ci, k3, x3);
+                }
+                for (; j < n; j += W) ai[j] = fma(-ci, ak[j], ai[j]);
                 if (w == k % W) ai[k] = -ci;
             }
         }
@@ -173,6 +187,18 @@ template <int TPE, int MAXR> __device__ void gj_invert(double* a, int n, int ld,
         for (int j = tid; j < n; j += TPE) a[k * ld + j] = (j == k) ? p : a[k * ld + j] * p;
         env_sync<TPE>(mask);
     }
+}
+
+// dot product of a matrix row with a vector, four independent accumulation chains
+__device__ __forceinline__ double row_dot(const double* m, const double* x, int n) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 3 < n; j += 4) {
+        a0 = fma(m[j], x[j], a0); a1 = fma(m[j + 1], x[j + 1], a1);
+        a2 = fma(m[j + 2], x[j + 2], a2); a3 = fma(m[j + 3], x[j + 3], a3);
+    }
+    for (; j < n; j++) a0 = fma(m[j], x[j], a0);
+    return (a0 + a1) + (a2 + a3);
 }
 
 // ------------------------------------------------------------------------------------------------ chronic access
@@ -298,36 +324,57 @@ __device__ __forceinline__ void compute_isolated(Env<TPE, D>& e) {
     env_sync<TPE>(e.mask);
 }
 
-// Line-end entries in the static substation adjacency order (c.adj): ebus[k] = bus this end sits on, or -1 when the
-// line is out of service; eoth[k] = bus of the other end.  A bus then walks the entries of its substation.
+// Per-bus lists of the in-service line ends that sit on the bus, rebuilt for every load-flow.  The entries of the two
+// buses of substation s share the substation's slice [adj_ptr[s], adj_ptr[s+1]) of the static adjacency: node 0 fills
+// it from the front, node 1 from the back.  Entry k: eoth = bus at the other end, eline = line*2+end, (eyr, eyi) =
+// the off-diagonal admittance seen from this end (yft from the origin, ytf from the extremity).
 template <int TPE, class D>
 __device__ __forceinline__ void build_entries(Env<TPE, D>& e, const PpnDevCase& c) {
-    for (int k = e.tid; k < 2 * e.N; k += TPE) {
-        const int a = c.adj[k], l = a >> 1, end = a & 1;
-        const bool on = e.status()[l] != 0;
-        e.ebus()[k] = on ? (end == 0 ? e.fbus()[l] : e.tbus()[l]) : (short)-1;
-        e.eoth()[k] = end == 0 ? e.tbus()[l] : e.fbus()[l];
+    const int S = e.S;
+    for (int b = e.tid; b < e.NB; b += TPE) {
+        const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
+        const int k0 = c.adj_ptr[s], k1 = c.adj_ptr[s + 1];
+        int n = 0;
+        for (int k = k0; k < k1; k++) {
+            const int a = c.adj[k], l = a >> 1, end = a & 1;
+            if (!e.status()[l] || (end == 0 ? e.onode()[l] : e.enode()[l]) != node) continue;
+            const int slot = node ? k1 - 1 - n : k0 + n;
+            const double* y = c.line_y + 8 * l + (end ? 4 : 2);
+            e.eoth()[slot] = end == 0 ? e.tbus()[l] : e.fbus()[l];
+            e.eline()[slot] = (short)a;
+            e.eyr()[slot] = y[0]; e.eyi()[slot] = y[1];
+            n++;
+        }
+        e.deg()[b] = (uint8_t)n;
     }
     env_sync<TPE>(e.mask);
 }
+
+// first entry slot and direction of bus b's list
+#define PPN_ENTRIES(e, c, b, k0, step)                                  \
+    const int _s = (b) >= (e).S ? (b) - (e).S : (b);                    \
+    const int step = (b) >= (e).S ? -1 : 1;                             \
+    const int k0 = (b) >= (e).S ? (c).adj_ptr[_s + 1] - 1 : (c).adj_ptr[_s];
 
 // S_b = V_b conj((Ybus V)_b), gathered per bus: diagonal term (ydr, ydi: shunt + own-end admittances) + the
 // off-diagonal entries of the in-service lines that end on this bus.
 template <int TPE, class D>
 __device__ __forceinline__ void bus_power(const Env<TPE, D>& e, const PpnDevCase& c, int b, double& sr, double& si) {
-    const int s = b >= e.S ? b - e.S : b;
+    PPN_ENTRIES(e, c, b, k0, step)
+    const int n = e.deg()[b];
     const double vr = e.vr()[b], vi = e.vi()[b];
     double ir = e.ydr()[b] * vr - e.ydi()[b] * vi, ii = e.ydr()[b] * vi + e.ydi()[b] * vr;
-    const int k1 = c.adj_ptr[s + 1];
-    for (int k = c.adj_ptr[s]; k < k1; k++) {
-        if (e.ebus()[k] != b) continue;
-        const int a = c.adj[k];
-        const double* y = c.line_y + 8 * (a >> 1) + ((a & 1) ? 4 : 2);   // ytf or yft
+    double jr = 0.0, ji = 0.0;   // second accumulator pair: two independent chains
+#pragma unroll 2
+    for (int q = 0; q < n; q++) {
+        const int k = k0 + step * q;
         const int o = e.eoth()[k];
+        const double yr = e.eyr()[k], yi = e.eyi()[k];
         const double wr = e.vr()[o], wi = e.vi()[o];
-        ir = fma(y[0], wr, fma(-y[1], wi, ir));
-        ii = fma(y[0], wi, fma(y[1], wr, ii));
+        if (q & 1) { jr = fma(yr, wr, fma(-yi, wi, jr)); ji = fma(yr, wi, fma(yi, wr, ji)); }
+        else { ir = fma(yr, wr, fma(-yi, wi, ir)); ii = fma(yr, wi, fma(yi, wr, ii)); }
     }
+    ir += jr; ii += ji;
     sr = vr * ir + vi * ii;   // V conj(I)
     si = vi * ir - vr * ii;
 }
@@ -342,30 +389,29 @@ __device__ __forceinline__ void bus_demand(const Env<TPE, D>& e, const PpnDevCas
     qd = here ? e.lqd()[l] : 0.0;
 }
 
-// fdpf's mismatch: mis = (V conj(Ybus V) - Sbus)/Vm; P over pv+pq, Q over pq; returns the two infinity norms.
+// fdpf's mismatch: mis = (V conj(Ybus V) - Sbus)/Vm; P over pv+pq, Q over pq.  Returns whether both infinity norms
+// are below tol (what fdpf tests after every half iteration); a NaN anywhere reads as "not converged".
 template <int TPE, class D>
-__device__ __forceinline__ void mismatch(Env<TPE, D>& e, const PpnDevCase& c, double& nP, double& nQ) {
-    double mp = 0.0, mq = 0.0;
+__device__ __forceinline__ bool mismatch(Env<TPE, D>& e, const PpnDevCase& c, double tol) {
+    bool open = false;
     for (int b = e.tid; b < e.NB; b += TPE) {
         const int t = e.btype()[b];
         if (t == PPN_BT_ISOLATED || t == PPN_BT_REF) continue;
         double sr, si;
         bus_power(e, c, b, sr, si);
-        const double vm = e.vm()[b];
-        const double p = (sr - e.pin()[b]) / vm;
+        const double rvm = 1.0 / e.vm()[b];
+        const double p = (sr - e.pin()[b]) * rvm;
         e.P()[e.idxp()[b]] = p;
-        const double ap = fabs(p);
-        mp = (ap > mp || ap != ap) ? ap : mp;
+        open |= !(fabs(p) < tol);
         if (t == PPN_BT_PQ) {
-            const double q = (si - e.qin()[b]) / vm;
+            const double q = (si - e.qin()[b]) * rvm;
             e.Q()[e.idxq()[b]] = q;
-            const double aq = fabs(q);
-            mq = (aq > mq || aq != aq) ? aq : mq;
+            open |= !(fabs(q) < tol);
         }
     }
-    nP = env_max_nan<TPE>(mp, e.redd(), e.tid, e.mask);
-    nQ = env_max_nan<TPE>(mq, e.redd() + (TPE + 31) / 32, e.tid, e.mask);
+    const bool any_open = env_any<TPE>(open, e.mask);
     env_sync<TPE>(e.mask);
+    return !any_open;
 }
 
 // One load-flow on the current topology/injections (grid.py:244-264 around runpf / rundcpf).  Returns true when the
@@ -483,12 +529,13 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
         const double va_ref = e.va()[ref] * (PPN_PI / 180.0);
         for (int i = tid; i < n1; i += TPE) {
             const int b = e.busp()[i];
-            const int s = b >= S ? b - S : b;
+            PPN_ENTRIES(e, c, b, k0, step)
+            const int nent = e.deg()[b];
             double diag = 0.0, bref = 0.0;
-            for (int k = c.adj_ptr[s]; k < c.adj_ptr[s + 1]; k++) {
-                if (e.ebus()[k] != b) continue;
+            for (int q = 0; q < nent; q++) {
+                const int k = k0 + step * q;
                 const int o = e.eoth()[k];
-                const double w = c.line_bdc[c.adj[k] >> 1];
+                const double w = c.line_bdc[e.eline()[k] >> 1];
                 diag += w;
                 if (o != ref) M1[i * ld1 + e.idxp()[o]] -= w; else bref -= w;
             }
@@ -499,9 +546,7 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
         env_sync<TPE>(mask);
         gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
         for (int i = tid; i < n1; i += TPE) {
-            double acc = 0.0;
-            for (int j = 0; j < n1; j++) acc = fma(M1[i * ld1 + j], e.P()[j], acc);
-            e.Q()[i] = acc;  // theta (radians) of pvpq bus i
+            e.Q()[i] = row_dot(M1 + i * ld1, e.P(), n1);  // theta (radians) of pvpq bus i
         }
         env_sync<TPE>(mask);
         for (int b = tid; b < NB; b += TPE) {
@@ -519,10 +564,11 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
         if (tid == 0) {
             // gen[refgen, PG] += (B[ref, :] Va - Pbus[ref]) baseMVA
             const int s = ref >= S ? ref - S : ref;
+            PPN_ENTRIES(e, c, ref, k0, step)
             double acc = 0.0;
-            for (int k = c.adj_ptr[s]; k < c.adj_ptr[s + 1]; k++) {
-                if (e.ebus()[k] != ref) continue;
-                acc += c.line_bdc[c.adj[k] >> 1] * (e.vr()[ref] - e.vr()[e.eoth()[k]]);
+            for (int q = 0; q < e.deg()[ref]; q++) {
+                const int k = k0 + step * q;
+                acc += c.line_bdc[e.eline()[k] >> 1] * (e.vr()[ref] - e.vr()[e.eoth()[k]]);
             }
             const int g = c.gen_of_sub[s];
             e.gpg()[g] = e.gpg()[g] + (acc - (e.pin()[ref] - c.bus_ysh_r[ref])) * c.base_mva;
@@ -560,22 +606,23 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
         for (int b = tid; b < NB; b += TPE) {
             const int t = e.btype()[b];
             if (t == PPN_BT_ISOLATED) continue;
-            const int s = b >= S ? b - S : b;
             const bool ispq = t == PPN_BT_PQ, inp = t != PPN_BT_REF;
             const int i = inp ? e.idxp()[b] : 0, iq = ispq ? e.idxq()[b] : 0;
             double d1 = 0.0, yr = c.bus_ysh_r[b], yi = c.bus_ysh_i[b];
-            for (int k = c.adj_ptr[s]; k < c.adj_ptr[s + 1]; k++) {
-                if (e.ebus()[k] != b) continue;
-                const int a = c.adj[k], l = a >> 1, end = a & 1;
+            PPN_ENTRIES(e, c, b, k0, step)
+            const int nent = e.deg()[b];
+            for (int q = 0; q < nent; q++) {
+                const int k = k0 + step * q;
+                const int a = e.eline()[k], l = a >> 1, end = a & 1;
                 const int o = e.eoth()[k];
                 const double w = c.line_bp[l];
-                const double* y = c.line_y + 8 * l;
-                yr += end == 0 ? y[0] : y[6];
-                yi += end == 0 ? y[1] : y[7];
+                const double* y = c.line_y + 8 * l + (end ? 6 : 0);   // ytt or yff
+                yr += y[0];
+                yi += y[1];
                 d1 += w;
                 const int to = e.btype()[o];
                 if (inp && to != PPN_BT_REF) M1[i * ld1 + e.idxp()[o]] -= w;
-                if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= (end == 0 ? y[3] : y[5]);
+                if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= e.eyi()[k];
             }
             e.ydr()[b] = yr; e.ydi()[b] = yi;
             if (inp) M1[i * ld1 + i] += d1;
@@ -589,9 +636,7 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
             if (half > 0) {
                 if (half & 1) {   // P iteration: Va[pvpq] -= B'^-1 P
                     for (int i = tid; i < n1; i += TPE) {
-                        double acc = 0.0;
-                        const double* mi = M1 + i * ld1;
-                        for (int j = 0; j < n1; j++) acc = fma(mi[j], e.P()[j], acc);
+                        const double acc = row_dot(M1 + i * ld1, e.P(), n1);
                         const int b = e.busp()[i];
                         const double va = e.va()[b] - acc;
                         double sn, cs;
@@ -601,9 +646,7 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
                     }
                 } else {          // Q iteration: Vm[pq] -= B''^-1 Q
                     for (int i = tid; i < n2; i += TPE) {
-                        double acc = 0.0;
-                        const double* mi = M2 + i * ld2;
-                        for (int j = 0; j < n2; j++) acc = fma(mi[j], e.Q()[j], acc);
+                        const double acc = row_dot(M2 + i * ld2, e.Q(), n2);
                         const int b = e.busq()[i];
                         const double vm = e.vm()[b] - acc;
                         e.vm()[b] = vm;
@@ -612,9 +655,7 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
                 }
                 env_sync<TPE>(mask);
             }
-            double nP, nQ;
-            mismatch(e, c, nP, nQ);
-            if (nP < cfg.tol && nQ < cfg.tol) { success = true; break; }
+            if (mismatch(e, c, cfg.tol)) { success = true; break; }
             if (half == 2 * cfg.max_it) break;
             if (half == 0) {
                 gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
@@ -814,8 +855,8 @@ __device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCa
 }
 
 // ------------------------------------------------------------------------------------------------------ the kernel
-template <int TPE, int MAXR, class D>
-__global__ void __launch_bounds__(TPE <= 32 ? 128 : TPE)
+template <int TPE, int MAXR, class D, int MINB>
+__global__ void __launch_bounds__(TPE <= 32 ? 64 : TPE, MINB)
 ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, PpnStepArgs args, int env_smem_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int envs_per_block = TPE <= 32 ? (blockDim.x / TPE) : 1;
@@ -1047,19 +1088,28 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
         atomicAdd(args.stats + 2, 1ull);
         atomicAdd(args.stats + 3, (unsigned long long)n_resets);
         atomicMax(args.stats + 4, (unsigned long long)depth);
+        atomicMax(args.stats + 5, (unsigned long long)n_lf);
+        atomicMax(args.stats + 6, (unsigned long long)n_it);
     }
 }
 
-template <int TPE, int MAXR, class D>
+template <int TPE, int MAXR, class D, int MINB>
 int launch_group(const PpnDevCase* c, const PpnDevChronics* ch, const PpnDevCfg* cfg, const PpnDevState* st,
                  const PpnStepArgs* args, int envs_per_block, int env_smem_bytes, cudaStream_t stream) {
     const int rows = args->n_envs * args->n_cand;
     const int epb = TPE <= 32 ? envs_per_block : 1;
     const int grid = (rows + epb - 1) / epb;
     const size_t smem = (size_t)epb * env_smem_bytes;
-    auto k = ppn_step_kernel<TPE, MAXR, D>;
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return (int)err;
+    auto k = ppn_step_kernel<TPE, MAXR, D, MINB>;
+    // opt in to large dynamic shared memory once per (kernel, device, size): the call costs more than a launch
+    static int configured_smem[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || configured_smem[dev] < (int)smem) {
+        cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        if (dev >= 0 && dev < 64) configured_smem[dev] = (int)smem;
+    }
     k<<<grid, TPE <= 32 ? epb * TPE : TPE, smem, stream>>>(*c, *ch, *cfg, *st, *args, env_smem_bytes);
     return (int)cudaGetLastError();
 }
@@ -1083,14 +1133,16 @@ extern "C" int ppn_launch_step(const PpnDevCase* c, const PpnDevChronics* ch, co
     if (args->n_envs * args->n_cand <= 0) return 0;
     switch (tpe) {
         case 16:
-            if (dims_match<Dims14>(c)) return launch_group<16, 2, Dims14>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
-            return launch_group<16, 2, DynDims>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+            if (dims_match<Dims14>(c)) return launch_group<16, 2, Dims14, 8>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+            return launch_group<16, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 32:
-            if (dims_match<Dims30>(c)) return launch_group<32, 2, Dims30>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
-            return launch_group<32, 2, DynDims>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+            // IEEE-14: 14 two-env CTAs per SM = 28 envs/SM, so that 4096 envs are one wave on 148 SMs
+            if (dims_match<Dims14>(c)) return launch_group<32, 2, Dims14, 14>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+            if (dims_match<Dims30>(c)) return launch_group<32, 2, Dims30, 5>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+            return launch_group<32, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 256:
-            if (dims_match<Dims118>(c)) return launch_group<256, 8, Dims118>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
-            return launch_group<256, 8, DynDims>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+            if (dims_match<Dims118>(c)) return launch_group<256, 8, Dims118, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+            return launch_group<256, 8, DynDims, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
         default: return (int)cudaErrorInvalidValue;
     }
 }

@@ -244,8 +244,8 @@ class VecRunEnv(object):
     def counters(self):
         """dict of cumulative device counters (load-flows, FD iterations, env steps, resets, max cascade depth) and
         launch information."""
-        out = (C.c_int64 * 8)()
+        out = (C.c_int64 * 10)()
         self._check(self.lib.ppn_get_counters(self.handle, out))
         keys = ('loadflows', 'fd_iterations', 'env_steps', 'resets', 'max_cascade_depth', 'kernel_launches',
-                'smem_bytes_per_env', 'threads_per_env')
+                'smem_bytes_per_env', 'threads_per_env', 'max_loadflows_one_env_step', 'max_fd_iterations_one_env_step')
         return dict(zip(keys, [int(v) for v in out]))
