@@ -49,24 +49,36 @@ def build_workload(grid, seed=0):
 
 
 def env_starts(n_envs, offset=0):
-    """env e plays chronic e mod 12 from row (e // 12) mod T (SURVEY.md 8d config 2)."""
-    e = np.arange(n_envs) + offset
-    return (e % N_CHRONICS).astype(np.int32), ((e // N_CHRONICS) % (N_ROWS - 1)).astype(np.int32)
+    """env e plays chronic e mod 12 from row (e // 12) mod (T - 1) (SURVEY.md 8d config 2); e is the GLOBAL index."""
+    from pypownet_b200.sharding import env_starts as starts
+    return starts(N_CHRONICS, N_ROWS, offset, offset + n_envs)
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (port)
-def _cpu_worker(args):
-    grid, env_id, n_steps, budget_s = args
+_WORKER = {}
+
+
+def _cpu_init(grid, counter):
+    """Pool initializer: every process builds the workload and ONE env once (as a reference process would)."""
     sys.path.insert(0, ROOT)
     from oracle.flat import FlatEnv, Config
+    with counter.get_lock():
+        env_id = counter.value
+        counter.value += 1
     case, cfg, chronics, imaps = build_workload(grid)
-    c, r = env_starts(1, env_id)
+    c, r = env_starts(1, 97 * env_id)
     env = FlatEnv(case, Config(cfg, reward_constant=float(case.n_sub), n_sub=case.n_sub), chronics,
                   start_id=int(c[0]), thermal_limits=imaps, start_row=int(r[0]))
     a = np.zeros(case.action_length, dtype=np.uint8)
     for _ in range(5):
         if env.step(a)[2]:
             env.process_game_over()
+    _WORKER['env'], _WORKER['action'] = env, a
+
+
+def _cpu_worker(args):
+    n_steps, budget_s = args
+    env, a = _WORKER['env'], _WORKER['action']
     t0 = time.perf_counter()
     done_steps = 0
     while done_steps < n_steps and (budget_s is None or time.perf_counter() - t0 < budget_s):
@@ -76,19 +88,20 @@ def _cpu_worker(args):
     return done_steps, time.perf_counter() - t0
 
 
-def cpu_baseline(grid, steps_per_proc, budget_s=None, pool=None, cores=None):
+def cpu_pool(grid, cores=None):
     cores = cores or os.cpu_count() or 1
-    own = pool is None
-    if own:
-        pool = mp.get_context('spawn').Pool(cores)
-    t0 = time.perf_counter()
-    res = pool.map(_cpu_worker, [(grid, 97 * i, steps_per_proc, budget_s) for i in range(cores)])
-    wall = time.perf_counter() - t0
-    if own:
-        pool.close()
+    ctx = mp.get_context('spawn')
+    pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(grid, ctx.Value('i', 0)))
+    pool.map(_cpu_worker, [(1, None)] * cores)          # make sure every process is up before anything is timed
+    return pool, cores
+
+
+def cpu_baseline(pool, cores, steps_per_proc, budget_s=None):
+    """All processes step their env concurrently; throughput = total env-steps / the slowest process' time."""
+    res = pool.map(_cpu_worker, [(steps_per_proc, budget_s)] * cores, chunksize=1)
     total = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
-    return total / busy, total, cores, wall
+    return total / busy, total, busy
 
 
 # ------------------------------------------------------------------------------------------------------ clock sampler
@@ -143,18 +156,16 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    per_step = 40                                        # env-steps per process per bench step (bounded sample)
-    pool = mp.get_context('spawn').Pool(cores)
+    per_step = 100                                       # env-steps per process per bench step (bounded sample)
+    pool, cores = cpu_pool(args.grid)
     for _ in range(args.warmup):
-        cpu_baseline(args.grid, 10, pool=pool, cores=cores)
-    t0 = time.perf_counter()
+        cpu_baseline(pool, cores, 10)
     total = 0
     busy = 0.0
     for _ in range(args.steps):
-        v, n, _, wall = cpu_baseline(args.grid, per_step, pool=pool, cores=cores)
+        v, n, b = cpu_baseline(pool, cores, per_step)
         total += n
-        busy += wall
+        busy += b
     pool.close()
     value = total / busy
     sample = '%d processes x %d do-nothing env-steps of %s per bench step, synthetic chronics' % (cores, per_step,
@@ -205,16 +216,14 @@ def run_b200(args):
                     start_chronics=sc, start_rows=sr)
     actions = torch.zeros((B, case.action_length), dtype=torch.uint8, device=dev)      # do-nothing agent
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    pack = torch.zeros((B, 7), dtype=torch.float64, device=dev)
-    gathered = torch.zeros((world * B, 7), dtype=torch.float64, device=dev) if world > 1 else None
+    from pypownet_b200 import sharding
+    pack = torch.zeros((B, sharding.PACK_WIDTH), dtype=torch.float64, device=dev)
+    gathered = torch.zeros((world * B, sharding.PACK_WIDTH), dtype=torch.float64, device=dev) if world > 1 else None
 
     def one_step():
         obs, reward, done, flag = env.step(actions, auto_reset=True)
         if world > 1:      # rewards / dones / flags of every shard on every rank (NCCL over NVLink)
-            pack[:, :5] = reward
-            pack[:, 5] = done
-            pack[:, 6] = flag
-            dist.all_gather_into_tensor(gathered, pack)
+            sharding.gather_results(sharding.pack_results(reward, done, flag, out=pack), world, out=gathered)
         return done
 
     for _ in range(max(args.warmup, 3)):
@@ -318,7 +327,9 @@ def run_b200(args):
                          'traffic': traffic, 'peak_source': peak_src, 'kernel': 'ppn_step_kernel',
                          'kernel_ms': kernel_ms}}
     if world == 1 and not args.no_cpu:
-        v, n, cores, wall_cpu = cpu_baseline(args.grid, 10 ** 9, budget_s=args.cpu_seconds)
+        pool, cores = cpu_pool(args.grid)
+        v, n, busy = cpu_baseline(pool, cores, 10 ** 9, budget_s=args.cpu_seconds)
+        pool.close()
         line['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
                                 'sample': '%d processes x %.0f s of do-nothing env-steps of %s (oracle/flat.py, the '
                                           'CPU restatement of the reference path), %d env-steps in total'

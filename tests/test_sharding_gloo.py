@@ -1,0 +1,71 @@
+"""World-size-2 test (gloo, CPU) of the host logic of the multi-GPU path: shard bounds, env start mapping and the
+per-step gather of packed rewards / dones / flags."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pypownet_b200 import sharding
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lo, hi = sharding.shard_bounds(n_total, rank, world)
+    B = hi - lo
+    g = torch.arange(lo, hi, dtype=torch.float64)
+    reward = torch.stack([g * k for k in range(1, 6)], dim=1)          # a function of the global env index
+    done = (torch.arange(lo, hi) % 3 == 0).to(torch.uint8)
+    flag = (torch.arange(lo, hi) % 5).to(torch.int32)
+    packed = sharding.pack_results(reward, done, flag)
+    out = sharding.gather_results(packed, world)
+    r, d, f = sharding.unpack_results(out)
+    q.put((rank, lo, hi, r.numpy(), d.numpy(), f.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_the_batch():
+    for n, w in ((4096, 1), (4096, 8), (10, 3), (7, 8)):
+        spans = [sharding.shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_env_starts_do_not_depend_on_the_number_of_shards():
+    whole = sharding.env_starts(12, 720, 0, 64)
+    parts = [sharding.env_starts(12, 720, *sharding.shard_bounds(64, r, 4)) for r in range(4)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), whole[0])
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), whole[1])
+
+
+def test_gather_of_packed_results_world_size_2():
+    world, n_total = 2, 12
+    port = _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = np.arange(n_total, dtype=np.float64)
+    for rank, lo, hi, r, d, f in res:
+        assert np.array_equal(r, np.stack([g * k for k in range(1, 6)], axis=1))
+        assert np.array_equal(d, (np.arange(n_total) % 3 == 0).astype(np.uint8))
+        assert np.array_equal(f, (np.arange(n_total) % 5).astype(np.int32))
