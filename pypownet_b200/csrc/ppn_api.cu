@@ -218,7 +218,7 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     int want = n1 * (n1 | 1) + n2 * (n2 | 1);
     const int worst = 2 * (NB - 1) * ((NB - 1) | 1);
     if (want > worst) want = worst;
-    env->envs_per_block = tpe == 16 ? 4 : 2;                 // 64-thread CTAs for the sub-warp / warp kernels
+    env->envs_per_block = tpe == 16 ? 4 : (tpe == 32 ? 2 : 1);   // 64-thread CTAs for the sub-warp / warp kernels
     int cap_bytes = max_smem / env->envs_per_block - fixed - 64;
     if (cap_bytes < 0) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "grid too large for the shared-memory plan"); }
     int cap = cap_bytes / 8;

@@ -582,9 +582,23 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
         success = true;
     } else {
         // ================= runpf, PF_ALG=2 (fast-decoupled XB)
+        // Every thread OWNS the buses tid, tid+TPE (one per thread for IEEE-14 and IEEE-118): their magnitude, angle,
+        // unit phasor, injections, Ybus diagonal and list position stay in registers for the whole iteration; only
+        // the rectangular voltages (read by neighbours) and the mismatch vectors (read by the solves) go through
+        // shared memory.
+        constexpr int RB = TPE <= 32 ? 2 : 1;
+        double r_vm[RB], r_va[RB], r_cs[RB], r_sn[RB], r_pin[RB], r_qin[RB], r_ydr[RB], r_ydi[RB], r_sr[RB], r_si[RB];
+        int r_t[RB], r_ip[RB], r_iq[RB], r_deg[RB], r_k0[RB], r_step[RB];
         // V0 from the stored state; on-line generators impose their set-point magnitude
-        for (int b = tid; b < NB; b += TPE) {
-            if (e.btype()[b] == PPN_BT_ISOLATED) continue;
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const int b = tid + r * TPE;
+            const int t = b < NB ? e.btype()[b] : PPN_BT_ISOLATED;
+            r_t[r] = t;
+            r_vm[r] = 1.0; r_va[r] = 0.0; r_cs[r] = 1.0; r_sn[r] = 0.0; r_pin[r] = 0.0; r_qin[r] = 0.0;
+            r_ydr[r] = 0.0; r_ydi[r] = 0.0; r_sr[r] = 0.0; r_si[r] = 0.0;
+            r_ip[r] = 0; r_iq[r] = 0; r_deg[r] = 0; r_k0[r] = 0; r_step[r] = 1;
+            if (t == PPN_BT_ISOLATED) continue;
             double sn, cs;
             sincos(e.va()[b] * (PPN_PI / 180.0), &sn, &cs);
             double vr = e.vm()[b] * cs, vi = e.vm()[b] * sn;
@@ -596,23 +610,29 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
             }
             e.vr()[b] = vr; e.vi()[b] = vi;
             const double vm = hypot(vr, vi);   // fdpf: Vm = abs(V0), Va = angle(V0)
-            e.vm()[b] = vm;
-            e.va()[b] = atan2(vi, vr);           // radians from here on
-            e.cs()[b] = cs; e.sn()[b] = sn;        // unit phasor of the current angle (refreshed by the P iteration)
+            r_vm[r] = vm;
+            r_va[r] = atan2(vi, vr);           // radians
+            r_cs[r] = vr / vm; r_sn[r] = vi / vm;
+            r_pin[r] = e.pin()[b]; r_qin[r] = e.qin()[b];
+            r_ip[r] = t != PPN_BT_REF ? e.idxp()[b] : 0;
+            r_iq[r] = t == PPN_BT_PQ ? e.idxq()[b] : 0;
+            r_deg[r] = e.deg()[b];
+            r_step[r] = b >= S ? -1 : 1;
+            r_k0[r] = b >= S ? c.adj_ptr[s + 1] - 1 : c.adj_ptr[s];
         }
         // B' (r = 0, no charging, no shunts, unit taps) over pv+pq; B'' = -Im(Ybus) over pq; Ybus diagonal
         for (int i = tid; i < n1 * ld1 + n2 * ld2; i += TPE) M1[i] = 0.0;
         env_sync<TPE>(mask);
-        for (int b = tid; b < NB; b += TPE) {
-            const int t = e.btype()[b];
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const int t = r_t[r];
             if (t == PPN_BT_ISOLATED) continue;
+            const int b = tid + r * TPE;
             const bool ispq = t == PPN_BT_PQ, inp = t != PPN_BT_REF;
-            const int i = inp ? e.idxp()[b] : 0, iq = ispq ? e.idxq()[b] : 0;
+            const int i = r_ip[r], iq = r_iq[r];
             double d1 = 0.0, yr = c.bus_ysh_r[b], yi = c.bus_ysh_i[b];
-            PPN_ENTRIES(e, c, b, k0, step)
-            const int nent = e.deg()[b];
-            for (int q = 0; q < nent; q++) {
-                const int k = k0 + step * q;
+            for (int q = 0; q < r_deg[r]; q++) {
+                const int k = r_k0[r] + r_step[r] * q;
                 const int a = e.eline()[k], l = a >> 1, end = a & 1;
                 const int o = e.eoth()[k];
                 const double w = c.line_bp[l];
@@ -624,7 +644,7 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
                 if (inp && to != PPN_BT_REF) M1[i * ld1 + e.idxp()[o]] -= w;
                 if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= e.eyi()[k];
             }
-            e.ydr()[b] = yr; e.ydi()[b] = yi;
+            r_ydr[r] = yr; r_ydi[r] = yi;
             if (inp) M1[i * ld1 + i] += d1;
             if (ispq) M2[iq * ld2 + iq] += -yi;
         }
@@ -634,28 +654,57 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
         int half = 0;
         while (true) {
             if (half > 0) {
-                if (half & 1) {   // P iteration: Va[pvpq] -= B'^-1 P
-                    for (int i = tid; i < n1; i += TPE) {
-                        const double acc = row_dot(M1 + i * ld1, e.P(), n1);
-                        const int b = e.busp()[i];
-                        const double va = e.va()[b] - acc;
-                        double sn, cs;
-                        sincos(va, &sn, &cs);
-                        e.va()[b] = va; e.cs()[b] = cs; e.sn()[b] = sn;
-                        e.vr()[b] = e.vm()[b] * cs; e.vi()[b] = e.vm()[b] * sn;
-                    }
-                } else {          // Q iteration: Vm[pq] -= B''^-1 Q
-                    for (int i = tid; i < n2; i += TPE) {
-                        const double acc = row_dot(M2 + i * ld2, e.Q(), n2);
-                        const int b = e.busq()[i];
-                        const double vm = e.vm()[b] - acc;
-                        e.vm()[b] = vm;
-                        e.vr()[b] = vm * e.cs()[b]; e.vi()[b] = vm * e.sn()[b];
+#pragma unroll
+                for (int r = 0; r < RB; r++) {
+                    const int t = r_t[r];
+                    const int b = tid + r * TPE;
+                    if (half & 1) {   // P iteration: Va[pvpq] -= B'^-1 P
+                        if (t == PPN_BT_PV || t == PPN_BT_PQ) {
+                            r_va[r] -= row_dot(M1 + r_ip[r] * ld1, e.P(), n1);
+                            sincos(r_va[r], &r_sn[r], &r_cs[r]);
+                            e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
+                        }
+                    } else if (t == PPN_BT_PQ) {   // Q iteration: Vm[pq] -= B''^-1 Q
+                        r_vm[r] -= row_dot(M2 + r_iq[r] * ld2, e.Q(), n2);
+                        e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
                     }
                 }
                 env_sync<TPE>(mask);
             }
-            if (mismatch(e, c, cfg.tol)) { success = true; break; }
+            // mismatch: mis = (V conj(Ybus V) - Sbus)/Vm, P over pv+pq, Q over pq; both infinity norms < tol ?
+            bool open = false;
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                const int t = r_t[r];
+                if (t != PPN_BT_PV && t != PPN_BT_PQ) continue;
+                const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
+                double ir = r_ydr[r] * vr - r_ydi[r] * vi, ii = r_ydr[r] * vi + r_ydi[r] * vr;
+                double jr = 0.0, ji = 0.0;
+#pragma unroll 2
+                for (int q = 0; q < r_deg[r]; q++) {
+                    const int k = r_k0[r] + r_step[r] * q;
+                    const int o = e.eoth()[k];
+                    const double yr = e.eyr()[k], yi = e.eyi()[k];
+                    const double wr = e.vr()[o], wi = e.vi()[o];
+                    if (q & 1) { jr = fma(yr, wr, fma(-yi, wi, jr)); ji = fma(yr, wi, fma(yi, wr, ji)); }
+                    else { ir = fma(yr, wr, fma(-yi, wi, ir)); ii = fma(yr, wi, fma(yi, wr, ii)); }
+                }
+                ir += jr; ii += ji;
+                const double sr = vr * ir + vi * ii, si = vi * ir - vr * ii;   // V conj(I)
+                r_sr[r] = sr; r_si[r] = si;
+                const double rvm = 1.0 / r_vm[r];
+                const double pm = (sr - r_pin[r]) * rvm;
+                e.P()[r_ip[r]] = pm;
+                open |= !(fabs(pm) < cfg.tol);
+                if (t == PPN_BT_PQ) {
+                    const double qm = (si - r_qin[r]) * rvm;
+                    e.Q()[r_iq[r]] = qm;
+                    open |= !(fabs(qm) < cfg.tol);
+                }
+            }
+            const bool any_open = env_any<TPE>(open, mask);
+            env_sync<TPE>(mask);
+            if (!any_open) { success = true; break; }
             if (half == 2 * cfg.max_it) break;
             if (half == 0) {
                 gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
@@ -663,17 +712,34 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
             }
             half++;
         }
-        const int it = (half + 1) / 2;
-        n_iter = it;
-        // ---- pfsoln
+        n_iter = (half + 1) / 2;
+        // ---- pfsoln: generator Q (and the slack's P) by the thread that owns the generator's bus
         int n_on = 0;
         for (int g = tid; g < e.G; g += TPE) n_on += (e.gstat()[g] > 0 && e.btype()[e.gbus()[g]] != PPN_BT_ISOLATED);
         n_on = env_sum_int<TPE>(n_on, e.redi(), tid, mask);
-        for (int g = tid; g < e.G; g += TPE) {
-            const int b = e.gbus()[g];
-            if (e.gstat()[g] > 0 && e.btype()[b] != PPN_BT_ISOLATED) {
-                double sr, si, pd, qd;
-                bus_power(e, c, b, sr, si);
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const int t = r_t[r];
+            if (t == PPN_BT_ISOLATED) continue;
+            const int b = tid + r * TPE;
+            const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
+            const int g = c.gen_of_sub[s];
+            if (g >= 0 && e.gnode()[g] == node && e.gstat()[g] > 0) {
+                double sr = r_sr[r], si = r_si[r];
+                if (t == PPN_BT_REF) {   // the reference bus is not part of the mismatch vectors
+                    const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
+                    double ir = r_ydr[r] * vr - r_ydi[r] * vi, ii = r_ydr[r] * vi + r_ydi[r] * vr;
+                    for (int q = 0; q < r_deg[r]; q++) {
+                        const int k = r_k0[r] + r_step[r] * q;
+                        const int o = e.eoth()[k];
+                        const double yr = e.eyr()[k], yi = e.eyi()[k];
+                        const double wr = e.vr()[o], wi = e.vi()[o];
+                        ir = fma(yr, wr, fma(-yi, wi, ir));
+                        ii = fma(yr, wi, fma(yi, wr, ii));
+                    }
+                    sr = vr * ir + vi * ii; si = vi * ir - vr * ii;
+                }
+                double pd, qd;
                 bus_demand(e, c, b, pd, qd);
                 double q = si * c.base_mva + qd;
                 if (n_on > 1) {
@@ -681,9 +747,14 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
                     if (qmin != qmax) q = qmin + ((q - qmin) / (qmax - qmin + 2.220446049250313e-16)) * (qmax - qmin);
                 }
                 e.gqg()[g] = q;
-                if (b == ref) e.gpg()[g] = sr * c.base_mva + pd;
+                if (t == PPN_BT_REF) e.gpg()[g] = sr * c.base_mva + pd;
             }
+            // adopted bus results: VM = |V|, VA = angle(V) in degrees
+            const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
+            e.vm()[b] = hypot(vr, vi);
+            e.va()[b] = atan2(vi, vr) * (180.0 / PPN_PI);
         }
+        env_sync<TPE>(mask);   // the branch results below reuse the storage of the mismatch vectors
         for (int l = tid; l < e.N; l += TPE) {
             double pf = 0.0, qf = 0.0, pt = 0.0, qt = 0.0;
             if (e.status()[l]) {
@@ -698,12 +769,6 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
                 pt = (tr * itr + ti * iti) * c.base_mva; qt = (ti * itr - tr * iti) * c.base_mva;
             }
             e.pf()[l] = pf; e.qf()[l] = qf; e.pt()[l] = pt; e.qt()[l] = qt;
-        }
-        env_sync<TPE>(mask);
-        for (int b = tid; b < NB; b += TPE) {
-            if (e.btype()[b] == PPN_BT_ISOLATED) continue;
-            e.vm()[b] = hypot(e.vr()[b], e.vi()[b]);
-            e.va()[b] = atan2(e.vi()[b], e.vr()[b]) * (180.0 / PPN_PI);
         }
     }
     // runpf tail: out-of-service generators report Pg = Qg = 0
