@@ -24,6 +24,16 @@
 #define PPN_SQRT3 1.7320508075688772
 #define PPN_PI 3.14159265358979323846
 
+#ifdef PPN_TIMING
+// Phase timing of the first load-flow of output row 0 (debug builds only: tools/phase_timing.py)
+__device__ long long ppn_timing_buf[64];
+#define PPN_TICK(id) do { if (slot == 0 && tid == 0 && ppn_timing_buf[63] == 0) ppn_timing_buf[id] = clock64(); } while (0)
+#define PPN_TICK_ACC(id, t0) do { if (slot == 0 && tid == 0 && ppn_timing_buf[63] == 0) ppn_timing_buf[id] += clock64() - (t0); } while (0)
+#else
+#define PPN_TICK(id)
+#define PPN_TICK_ACC(id, t0)
+#endif
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------- env-wide primitives
@@ -187,6 +197,61 @@ template <int TPE, int MAXR> __device__ void gj_invert(double* a, int n, int ld,
         for (int j = tid; j < n; j += TPE) a[k * ld + j] = (j == k) ? p : a[k * ld + j] * p;
         env_sync<TPE>(mask);
     }
+}
+
+// Explicit shared-memory accesses (32-bit shared-window addresses): the matrices may also live in the HBM workspace,
+// so their pointers are generic; these keep the common in-shared-memory path on LDS/STS.
+__device__ __forceinline__ unsigned saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds64(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// Gauss-Jordan inverse of a matrix in SHARED memory with every row held in the registers of one lane.  Per pivot
+// step the pivot row goes through a small shared buffer (one store by its owner, broadcast loads by everyone) and the
+// rank-1 update runs on registers.  `i` = row of this lane, `nsteps` is uniform over `syncmask` (max n of the
+// matrices inverted side by side), `piv_s` = NR doubles per matrix.  Same operation order as gj_invert.
+// NR = 16: pivot steps fully unrolled (static register indices, no select chains); two matrices fit one warp.
+__device__ __noinline__ void gj16_rows_in_registers(unsigned m_s, int n, int ld, int i, int nsteps, unsigned piv_s,
+                                                    unsigned syncmask) {
+    double row[16];
+    const bool mine = i < n;
+#pragma unroll
+    for (int j = 0; j < 16; j++) row[j] = (mine && j < n) ? lds64(m_s + 8u * (unsigned)(i * ld + j)) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < nsteps) {
+            if (mine && i == k) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) sts64(piv_s + 8u * j, row[j]);
+            }
+            __syncwarp(syncmask);
+            if (mine && k < n) {
+                const double p = 1.0 / lds64(piv_s + 8u * k);
+                if (i == k) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) row[j] = (j == k) ? p : row[j] * p;
+                } else {
+                    const double ci = row[k] * p;
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (j != k) row[j] = fma(-ci, lds64(piv_s + 8u * j), row[j]);
+                    row[k] = -ci;
+                }
+            }
+            __syncwarp(syncmask);
+        }
+    }
+    if (mine) {
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if (j < n) sts64(m_s + 8u * (unsigned)(i * ld + j), row[j]);
+    }
+    __syncwarp(syncmask);
 }
 
 // dot product of a matrix row with a vector, four independent accumulation chains
@@ -414,6 +479,298 @@ __device__ __forceinline__ bool mismatch(Env<TPE, D>& e, const PpnDevCase& c, do
     return !any_open;
 }
 
+// rundcpf on the prepared env: B theta = Pbus on pv+pq, Vm := 1.  M1 = n1 x n1 work matrix.
+template <int TPE, int MAXR, class D>
+__device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, double* M1, int n1, int ld1, int ref) {
+    const int NB = e.NB, S = e.S, tid = e.tid;
+    const unsigned mask = e.mask;
+    bool success;
+    // ================= rundcpf: B theta = Pbus on pv+pq, Vm := 1
+    for (int i = tid; i < n1 * ld1; i += TPE) M1[i] = 0.0;
+    env_sync<TPE>(mask);
+    const double va_ref = e.va()[ref] * (PPN_PI / 180.0);
+    for (int i = tid; i < n1; i += TPE) {
+        const int b = e.busp()[i];
+        PPN_ENTRIES(e, c, b, k0, step)
+        const int nent = e.deg()[b];
+        double diag = 0.0, bref = 0.0;
+        for (int q = 0; q < nent; q++) {
+            const int k = k0 + step * q;
+            const int o = e.eoth()[k];
+            const double w = c.line_bdc[e.eline()[k] >> 1];
+            diag += w;
+            if (o != ref) M1[i * ld1 + e.idxp()[o]] -= w; else bref -= w;
+        }
+        M1[i * ld1 + i] += diag;
+        // rhs = Pbus[pvpq] - B[pvpq, ref] Va0[ref], Pbus = Re(Sbus) - Gs/baseMVA
+        e.P()[i] = (e.pin()[b] - c.bus_ysh_r[b]) - bref * va_ref;
+    }
+    env_sync<TPE>(mask);
+    gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
+    for (int i = tid; i < n1; i += TPE) {
+        e.Q()[i] = row_dot(M1 + i * ld1, e.P(), n1);  // theta (radians) of pvpq bus i
+    }
+    env_sync<TPE>(mask);
+    for (int b = tid; b < NB; b += TPE) {
+        const int t = e.btype()[b];
+        if (t == PPN_BT_ISOLATED) continue;
+        e.vr()[b] = (t == PPN_BT_REF) ? va_ref : e.Q()[e.idxp()[b]];  // vr holds theta in DC mode
+    }
+    env_sync<TPE>(mask);
+    // branch flows, slack production
+    for (int l = tid; l < e.N; l += TPE) {
+        double p = 0.0;
+        if (e.status()[l]) p = c.line_bdc[l] * (e.vr()[e.fbus()[l]] - e.vr()[e.tbus()[l]]) * c.base_mva;
+        e.pf()[l] = p; e.pt()[l] = -p; e.qf()[l] = 0.0; e.qt()[l] = 0.0;
+    }
+    if (tid == 0) {
+        // gen[refgen, PG] += (B[ref, :] Va - Pbus[ref]) baseMVA
+        const int s = ref >= S ? ref - S : ref;
+        PPN_ENTRIES(e, c, ref, k0, step)
+        double acc = 0.0;
+        for (int q = 0; q < e.deg()[ref]; q++) {
+            const int k = k0 + step * q;
+            acc += c.line_bdc[e.eline()[k] >> 1] * (e.vr()[ref] - e.vr()[e.eoth()[k]]);
+        }
+        const int g = c.gen_of_sub[s];
+        e.gpg()[g] = e.gpg()[g] + (acc - (e.pin()[ref] - c.bus_ysh_r[ref])) * c.base_mva;
+    }
+    env_sync<TPE>(mask);
+    for (int b = tid; b < NB; b += TPE) {
+        if (e.btype()[b] == PPN_BT_ISOLATED) continue;
+        e.vm()[b] = 1.0;
+        e.va()[b] = e.vr()[b] * (180.0 / PPN_PI);
+    }
+    success = true;
+    return success;
+}
+
+// runpf with PF_ALG=2 (fast-decoupled XB, fdpf + pfsoln of SURVEY.md Appendix A) on the prepared env.  M1 / M2 hold
+// B' (n1 x n1) and B'' (n2 x n2); SMEM says whether they are in shared memory (the common case: the accesses then
+// compile to LDS/STS) or in the env's slice of the HBM workspace.
+template <int TPE, int MAXR, class D, bool SMEM>
+__device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevCfg& cfg, double* M1, double* M2,
+                                         int n1, int n2, int ld1, int ld2, int ref, int slot, int& n_iter) {
+    const int NB = e.NB, S = e.S, tid = e.tid;
+    const unsigned mask = e.mask;
+    bool success;
+    // ================= runpf, PF_ALG=2 (fast-decoupled XB)
+    // Every thread OWNS the buses tid, tid+TPE (one per thread for IEEE-14 and IEEE-118): their magnitude, angle,
+    // unit phasor, injections, Ybus diagonal and list position stay in registers for the whole iteration; only
+    // the rectangular voltages (read by neighbours) and the mismatch vectors (read by the solves) go through
+    // shared memory.
+    constexpr int RB = TPE <= 32 ? 2 : 1;
+    double r_vm[RB], r_va[RB], r_cs[RB], r_sn[RB], r_pin[RB], r_qin[RB], r_ydr[RB], r_ydi[RB], r_sr[RB], r_si[RB];
+    int r_t[RB], r_ip[RB], r_iq[RB], r_deg[RB], r_k0[RB], r_step[RB];
+    PPN_TICK(4);
+    // V0 from the stored state; on-line generators impose their set-point magnitude
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        const int b = tid + r * TPE;
+        const int t = b < NB ? e.btype()[b] : PPN_BT_ISOLATED;
+        r_t[r] = t;
+        r_vm[r] = 1.0; r_va[r] = 0.0; r_cs[r] = 1.0; r_sn[r] = 0.0; r_pin[r] = 0.0; r_qin[r] = 0.0;
+        r_ydr[r] = 0.0; r_ydi[r] = 0.0; r_sr[r] = 0.0; r_si[r] = 0.0;
+        r_ip[r] = 0; r_iq[r] = 0; r_deg[r] = 0; r_k0[r] = 0; r_step[r] = 1;
+        if (t == PPN_BT_ISOLATED) continue;
+        double sn, cs;
+        sincos(e.va()[b] * (PPN_PI / 180.0), &sn, &cs);
+        double vr = e.vm()[b] * cs, vi = e.vm()[b] * sn;
+        const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
+        const int g = c.gen_of_sub[s];
+        if (g >= 0 && e.gnode()[g] == node && e.gstat()[g] > 0) {
+            const double sc = e.gvg()[g] / hypot(vr, vi);
+            vr *= sc; vi *= sc;
+        }
+        e.vr()[b] = vr; e.vi()[b] = vi;
+        const double vm = hypot(vr, vi);   // fdpf: Vm = abs(V0), Va = angle(V0)
+        r_vm[r] = vm;
+        r_va[r] = atan2(vi, vr);           // radians
+        r_cs[r] = vr / vm; r_sn[r] = vi / vm;
+        r_pin[r] = e.pin()[b]; r_qin[r] = e.qin()[b];
+        r_ip[r] = t != PPN_BT_REF ? e.idxp()[b] : 0;
+        r_iq[r] = t == PPN_BT_PQ ? e.idxq()[b] : 0;
+        r_deg[r] = e.deg()[b];
+        r_step[r] = b >= S ? -1 : 1;
+        r_k0[r] = b >= S ? c.adj_ptr[s + 1] - 1 : c.adj_ptr[s];
+    }
+    PPN_TICK(5);
+    // B' (r = 0, no charging, no shunts, unit taps) over pv+pq; B'' = -Im(Ybus) over pq; Ybus diagonal
+    for (int i = tid; i < n1 * ld1 + n2 * ld2; i += TPE) M1[i] = 0.0;
+    env_sync<TPE>(mask);
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        const int t = r_t[r];
+        if (t == PPN_BT_ISOLATED) continue;
+        const int b = tid + r * TPE;
+        const bool ispq = t == PPN_BT_PQ, inp = t != PPN_BT_REF;
+        const int i = r_ip[r], iq = r_iq[r];
+        double d1 = 0.0, yr = c.bus_ysh_r[b], yi = c.bus_ysh_i[b];
+        for (int q = 0; q < r_deg[r]; q++) {
+            const int k = r_k0[r] + r_step[r] * q;
+            const int a = e.eline()[k], l = a >> 1, end = a & 1;
+            const int o = e.eoth()[k];
+            const double w = c.line_bp[l];
+            const double* y = c.line_y + 8 * l + (end ? 6 : 0);   // ytt or yff
+            yr += y[0];
+            yi += y[1];
+            d1 += w;
+            const int to = e.btype()[o];
+            if (inp && to != PPN_BT_REF) M1[i * ld1 + e.idxp()[o]] -= w;
+            if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= e.eyi()[k];
+        }
+        r_ydr[r] = yr; r_ydi[r] = yi;
+        if (inp) M1[i * ld1 + i] += d1;
+        if (ispq) M2[iq * ld2 + iq] += -yi;
+    }
+    env_sync<TPE>(mask);
+    // fdpf: evaluate, then alternate P (angle) and Q (magnitude) half-iterations, testing after each
+    PPN_TICK(6);
+    success = false;
+    int half = 0;
+    while (true) {
+#ifdef PPN_TIMING
+        long long t_a = clock64();
+#endif
+        if (half > 0) {
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                const int t = r_t[r];
+                const int b = tid + r * TPE;
+                if (half & 1) {   // P iteration: Va[pvpq] -= B'^-1 P
+                    if (t == PPN_BT_PV || t == PPN_BT_PQ) {
+                        r_va[r] -= row_dot(M1 + r_ip[r] * ld1, e.P(), n1);
+                        sincos(r_va[r], &r_sn[r], &r_cs[r]);
+                        e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
+                    }
+                } else if (t == PPN_BT_PQ) {   // Q iteration: Vm[pq] -= B''^-1 Q
+                    r_vm[r] -= row_dot(M2 + r_iq[r] * ld2, e.Q(), n2);
+                    e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
+                }
+            }
+            env_sync<TPE>(mask);
+        }
+        PPN_TICK_ACC(20 + (half & 1), t_a);   // update half-steps: [20] Q, [21] P
+#ifdef PPN_TIMING
+        long long t_b = clock64();
+#endif
+        // mismatch: mis = (V conj(Ybus V) - Sbus)/Vm, P over pv+pq, Q over pq; both infinity norms < tol ?
+        bool open = false;
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const int t = r_t[r];
+            if (t != PPN_BT_PV && t != PPN_BT_PQ) continue;
+            const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
+            double ir = r_ydr[r] * vr - r_ydi[r] * vi, ii = r_ydr[r] * vi + r_ydi[r] * vr;
+            double jr = 0.0, ji = 0.0;
+#pragma unroll 2
+            for (int q = 0; q < r_deg[r]; q++) {
+                const int k = r_k0[r] + r_step[r] * q;
+                const int o = e.eoth()[k];
+                const double yr = e.eyr()[k], yi = e.eyi()[k];
+                const double wr = e.vr()[o], wi = e.vi()[o];
+                if (q & 1) { jr = fma(yr, wr, fma(-yi, wi, jr)); ji = fma(yr, wi, fma(yi, wr, ji)); }
+                else { ir = fma(yr, wr, fma(-yi, wi, ir)); ii = fma(yr, wi, fma(yi, wr, ii)); }
+            }
+            ir += jr; ii += ji;
+            const double sr = vr * ir + vi * ii, si = vi * ir - vr * ii;   // V conj(I)
+            r_sr[r] = sr; r_si[r] = si;
+            const double rvm = 1.0 / r_vm[r];
+            const double pm = (sr - r_pin[r]) * rvm;
+            e.P()[r_ip[r]] = pm;
+            open |= !(fabs(pm) < cfg.tol);
+            if (t == PPN_BT_PQ) {
+                const double qm = (si - r_qin[r]) * rvm;
+                e.Q()[r_iq[r]] = qm;
+                open |= !(fabs(qm) < cfg.tol);
+            }
+        }
+        const bool any_open = env_any<TPE>(open, mask);
+        env_sync<TPE>(mask);
+        PPN_TICK_ACC(22, t_b);                  // mismatch evaluations
+        if (!any_open) { success = true; break; }
+        if (half == 2 * cfg.max_it) break;
+        if (half == 0) {
+            PPN_TICK(7);
+            if (TPE == 32 && SMEM && n1 <= 16 && n2 <= 16) {
+                // both inverses at once: lanes 0-15 hold the rows of B', lanes 16-31 those of B''
+                const int hf = tid >> 4;
+                gj16_rows_in_registers(saddr(hf ? M2 : M1), hf ? n2 : n1, hf ? ld2 : ld1, tid & 15,
+                                       n1 > n2 ? n1 : n2, saddr(hf ? e.ydi() : e.ydr()), mask);
+            } else {
+                gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
+                gj_invert<TPE, MAXR>(M2, n2, ld2, tid, mask);
+            }
+            PPN_TICK(8);
+            PPN_TICK(9);
+        }
+        half++;
+    }
+    n_iter = (half + 1) / 2;
+    PPN_TICK(10);
+#ifdef PPN_TIMING
+    if (slot == 0 && tid == 0 && ppn_timing_buf[63] == 0) { ppn_timing_buf[30] = half; ppn_timing_buf[31] = n1; ppn_timing_buf[32] = n2; }
+#endif
+    // ---- pfsoln: generator Q (and the slack's P) by the thread that owns the generator's bus
+    int n_on = 0;
+    for (int g = tid; g < e.G; g += TPE) n_on += (e.gstat()[g] > 0 && e.btype()[e.gbus()[g]] != PPN_BT_ISOLATED);
+    n_on = env_sum_int<TPE>(n_on, e.redi(), tid, mask);
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        const int t = r_t[r];
+        if (t == PPN_BT_ISOLATED) continue;
+        const int b = tid + r * TPE;
+        const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
+        const int g = c.gen_of_sub[s];
+        if (g >= 0 && e.gnode()[g] == node && e.gstat()[g] > 0) {
+            double sr = r_sr[r], si = r_si[r];
+            if (t == PPN_BT_REF) {   // the reference bus is not part of the mismatch vectors
+                const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
+                double ir = r_ydr[r] * vr - r_ydi[r] * vi, ii = r_ydr[r] * vi + r_ydi[r] * vr;
+                for (int q = 0; q < r_deg[r]; q++) {
+                    const int k = r_k0[r] + r_step[r] * q;
+                    const int o = e.eoth()[k];
+                    const double yr = e.eyr()[k], yi = e.eyi()[k];
+                    const double wr = e.vr()[o], wi = e.vi()[o];
+                    ir = fma(yr, wr, fma(-yi, wi, ir));
+                    ii = fma(yr, wi, fma(yi, wr, ii));
+                }
+                sr = vr * ir + vi * ii; si = vi * ir - vr * ii;
+            }
+            double pd, qd;
+            bus_demand(e, c, b, pd, qd);
+            double q = si * c.base_mva + qd;
+            if (n_on > 1) {
+                const double qmin = c.gen_qmin[g], qmax = c.gen_qmax[g];
+                if (qmin != qmax) q = qmin + ((q - qmin) / (qmax - qmin + 2.220446049250313e-16)) * (qmax - qmin);
+            }
+            e.gqg()[g] = q;
+            if (t == PPN_BT_REF) e.gpg()[g] = sr * c.base_mva + pd;
+        }
+        // adopted bus results: VM = |V|, VA = angle(V) in degrees
+        const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
+        e.vm()[b] = hypot(vr, vi);
+        e.va()[b] = atan2(vi, vr) * (180.0 / PPN_PI);
+    }
+    env_sync<TPE>(mask);   // the branch results below reuse the storage of the mismatch vectors
+    for (int l = tid; l < e.N; l += TPE) {
+        double pf = 0.0, qf = 0.0, pt = 0.0, qt = 0.0;
+        if (e.status()[l]) {
+            const double* y = c.line_y + 8 * l;
+            const int f = e.fbus()[l], t = e.tbus()[l];
+            const double fr = e.vr()[f], fi = e.vi()[f], tr = e.vr()[t], ti = e.vi()[t];
+            const double ifr = y[0] * fr - y[1] * fi + y[2] * tr - y[3] * ti;
+            const double ifi = y[0] * fi + y[1] * fr + y[2] * ti + y[3] * tr;
+            const double itr = y[4] * fr - y[5] * fi + y[6] * tr - y[7] * ti;
+            const double iti = y[4] * fi + y[5] * fr + y[6] * ti + y[7] * tr;
+            pf = (fr * ifr + fi * ifi) * c.base_mva; qf = (fi * ifr - fr * ifi) * c.base_mva;
+            pt = (tr * itr + ti * iti) * c.base_mva; qt = (ti * itr - tr * iti) * c.base_mva;
+        }
+        e.pf()[l] = pf; e.qf()[l] = qf; e.pt()[l] = pt; e.qt()[l] = qt;
+    }
+    return success;
+}
+
 // One load-flow on the current topology/injections (grid.py:244-264 around runpf / rundcpf).  Returns true when the
 // reference raises DivergingLoadflowException.  On success the state (vm, va in degrees, gen pg/qg, flows) is the
 // adopted output (`self.mpc = output`, grid.py:260).
@@ -423,6 +780,7 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
     const int NB = e.NB, S = e.S, tid = e.tid;
     const unsigned mask = e.mask;
     n_iter = 0;
+    PPN_TICK(0);
     compute_isolated(e);  // mark = isolated
     // ---- _synchronize_bus_types (grid.py:140-174) folded with bustypes: a bus whose generator is off is PQ
     int slack = c.slack_bus;
@@ -476,6 +834,7 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
     }
     env_sync<TPE>(mask);
     const int ref = e.misc()[0], n1 = e.misc()[1], n2 = e.misc()[2];
+    PPN_TICK(1);
     if (ref < 0) return true;
     // ---- connectivity: every non-isolated bus must be reachable from the reference bus over in-service lines
     for (int b = tid; b < NB; b += TPE) e.mark()[b] = (b == ref) ? 1 : 0;   // mark = reached
@@ -502,8 +861,10 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
         return true;
     }
     if (n1 == 0 || (n2 == 0 && !cfg.dc)) return true;
+    PPN_TICK(2);
     // ---- per-bus demand and makeSbus
     build_entries(e, c);
+    PPN_TICK(3);
     for (int b = tid; b < NB; b += TPE) {
         if (e.btype()[b] == PPN_BT_ISOLATED) continue;
         const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
@@ -518,259 +879,17 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
     }
     // ---- matrices: shared memory when they fit, else the env's slice of the global workspace
     const int ld1 = n1 | 1, ld2 = n2 | 1;
-    double *M1, *M2;
-    if (n1 * ld1 + n2 * ld2 <= args.mat_cap) { M1 = e.mat(); M2 = M1 + n1 * ld1; }
-    else { M1 = args.ws + (size_t)slot * args.ws_stride; M2 = M1 + n1 * ld1; }
     bool success;
-    if (cfg.dc) {
-        // ================= rundcpf: B theta = Pbus on pv+pq, Vm := 1
-        for (int i = tid; i < n1 * ld1; i += TPE) M1[i] = 0.0;
-        env_sync<TPE>(mask);
-        const double va_ref = e.va()[ref] * (PPN_PI / 180.0);
-        for (int i = tid; i < n1; i += TPE) {
-            const int b = e.busp()[i];
-            PPN_ENTRIES(e, c, b, k0, step)
-            const int nent = e.deg()[b];
-            double diag = 0.0, bref = 0.0;
-            for (int q = 0; q < nent; q++) {
-                const int k = k0 + step * q;
-                const int o = e.eoth()[k];
-                const double w = c.line_bdc[e.eline()[k] >> 1];
-                diag += w;
-                if (o != ref) M1[i * ld1 + e.idxp()[o]] -= w; else bref -= w;
-            }
-            M1[i * ld1 + i] += diag;
-            // rhs = Pbus[pvpq] - B[pvpq, ref] Va0[ref], Pbus = Re(Sbus) - Gs/baseMVA
-            e.P()[i] = (e.pin()[b] - c.bus_ysh_r[b]) - bref * va_ref;
-        }
-        env_sync<TPE>(mask);
-        gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
-        for (int i = tid; i < n1; i += TPE) {
-            e.Q()[i] = row_dot(M1 + i * ld1, e.P(), n1);  // theta (radians) of pvpq bus i
-        }
-        env_sync<TPE>(mask);
-        for (int b = tid; b < NB; b += TPE) {
-            const int t = e.btype()[b];
-            if (t == PPN_BT_ISOLATED) continue;
-            e.vr()[b] = (t == PPN_BT_REF) ? va_ref : e.Q()[e.idxp()[b]];  // vr holds theta in DC mode
-        }
-        env_sync<TPE>(mask);
-        // branch flows, slack production
-        for (int l = tid; l < e.N; l += TPE) {
-            double p = 0.0;
-            if (e.status()[l]) p = c.line_bdc[l] * (e.vr()[e.fbus()[l]] - e.vr()[e.tbus()[l]]) * c.base_mva;
-            e.pf()[l] = p; e.pt()[l] = -p; e.qf()[l] = 0.0; e.qt()[l] = 0.0;
-        }
-        if (tid == 0) {
-            // gen[refgen, PG] += (B[ref, :] Va - Pbus[ref]) baseMVA
-            const int s = ref >= S ? ref - S : ref;
-            PPN_ENTRIES(e, c, ref, k0, step)
-            double acc = 0.0;
-            for (int q = 0; q < e.deg()[ref]; q++) {
-                const int k = k0 + step * q;
-                acc += c.line_bdc[e.eline()[k] >> 1] * (e.vr()[ref] - e.vr()[e.eoth()[k]]);
-            }
-            const int g = c.gen_of_sub[s];
-            e.gpg()[g] = e.gpg()[g] + (acc - (e.pin()[ref] - c.bus_ysh_r[ref])) * c.base_mva;
-        }
-        env_sync<TPE>(mask);
-        for (int b = tid; b < NB; b += TPE) {
-            if (e.btype()[b] == PPN_BT_ISOLATED) continue;
-            e.vm()[b] = 1.0;
-            e.va()[b] = e.vr()[b] * (180.0 / PPN_PI);
-        }
-        success = true;
+    if (n1 * ld1 + n2 * ld2 <= args.mat_cap) {
+        double* M1 = e.mat();
+        success = cfg.dc ? dc_solve<TPE, MAXR, D>(e, c, M1, n1, ld1, ref)
+                         : ac_solve<TPE, MAXR, D, true>(e, c, cfg, M1, M1 + n1 * ld1, n1, n2, ld1, ld2, ref, slot, n_iter);
     } else {
-        // ================= runpf, PF_ALG=2 (fast-decoupled XB)
-        // Every thread OWNS the buses tid, tid+TPE (one per thread for IEEE-14 and IEEE-118): their magnitude, angle,
-        // unit phasor, injections, Ybus diagonal and list position stay in registers for the whole iteration; only
-        // the rectangular voltages (read by neighbours) and the mismatch vectors (read by the solves) go through
-        // shared memory.
-        constexpr int RB = TPE <= 32 ? 2 : 1;
-        double r_vm[RB], r_va[RB], r_cs[RB], r_sn[RB], r_pin[RB], r_qin[RB], r_ydr[RB], r_ydi[RB], r_sr[RB], r_si[RB];
-        int r_t[RB], r_ip[RB], r_iq[RB], r_deg[RB], r_k0[RB], r_step[RB];
-        // V0 from the stored state; on-line generators impose their set-point magnitude
-#pragma unroll
-        for (int r = 0; r < RB; r++) {
-            const int b = tid + r * TPE;
-            const int t = b < NB ? e.btype()[b] : PPN_BT_ISOLATED;
-            r_t[r] = t;
-            r_vm[r] = 1.0; r_va[r] = 0.0; r_cs[r] = 1.0; r_sn[r] = 0.0; r_pin[r] = 0.0; r_qin[r] = 0.0;
-            r_ydr[r] = 0.0; r_ydi[r] = 0.0; r_sr[r] = 0.0; r_si[r] = 0.0;
-            r_ip[r] = 0; r_iq[r] = 0; r_deg[r] = 0; r_k0[r] = 0; r_step[r] = 1;
-            if (t == PPN_BT_ISOLATED) continue;
-            double sn, cs;
-            sincos(e.va()[b] * (PPN_PI / 180.0), &sn, &cs);
-            double vr = e.vm()[b] * cs, vi = e.vm()[b] * sn;
-            const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
-            const int g = c.gen_of_sub[s];
-            if (g >= 0 && e.gnode()[g] == node && e.gstat()[g] > 0) {
-                const double sc = e.gvg()[g] / hypot(vr, vi);
-                vr *= sc; vi *= sc;
-            }
-            e.vr()[b] = vr; e.vi()[b] = vi;
-            const double vm = hypot(vr, vi);   // fdpf: Vm = abs(V0), Va = angle(V0)
-            r_vm[r] = vm;
-            r_va[r] = atan2(vi, vr);           // radians
-            r_cs[r] = vr / vm; r_sn[r] = vi / vm;
-            r_pin[r] = e.pin()[b]; r_qin[r] = e.qin()[b];
-            r_ip[r] = t != PPN_BT_REF ? e.idxp()[b] : 0;
-            r_iq[r] = t == PPN_BT_PQ ? e.idxq()[b] : 0;
-            r_deg[r] = e.deg()[b];
-            r_step[r] = b >= S ? -1 : 1;
-            r_k0[r] = b >= S ? c.adj_ptr[s + 1] - 1 : c.adj_ptr[s];
-        }
-        // B' (r = 0, no charging, no shunts, unit taps) over pv+pq; B'' = -Im(Ybus) over pq; Ybus diagonal
-        for (int i = tid; i < n1 * ld1 + n2 * ld2; i += TPE) M1[i] = 0.0;
-        env_sync<TPE>(mask);
-#pragma unroll
-        for (int r = 0; r < RB; r++) {
-            const int t = r_t[r];
-            if (t == PPN_BT_ISOLATED) continue;
-            const int b = tid + r * TPE;
-            const bool ispq = t == PPN_BT_PQ, inp = t != PPN_BT_REF;
-            const int i = r_ip[r], iq = r_iq[r];
-            double d1 = 0.0, yr = c.bus_ysh_r[b], yi = c.bus_ysh_i[b];
-            for (int q = 0; q < r_deg[r]; q++) {
-                const int k = r_k0[r] + r_step[r] * q;
-                const int a = e.eline()[k], l = a >> 1, end = a & 1;
-                const int o = e.eoth()[k];
-                const double w = c.line_bp[l];
-                const double* y = c.line_y + 8 * l + (end ? 6 : 0);   // ytt or yff
-                yr += y[0];
-                yi += y[1];
-                d1 += w;
-                const int to = e.btype()[o];
-                if (inp && to != PPN_BT_REF) M1[i * ld1 + e.idxp()[o]] -= w;
-                if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= e.eyi()[k];
-            }
-            r_ydr[r] = yr; r_ydi[r] = yi;
-            if (inp) M1[i * ld1 + i] += d1;
-            if (ispq) M2[iq * ld2 + iq] += -yi;
-        }
-        env_sync<TPE>(mask);
-        // fdpf: evaluate, then alternate P (angle) and Q (magnitude) half-iterations, testing after each
-        success = false;
-        int half = 0;
-        while (true) {
-            if (half > 0) {
-#pragma unroll
-                for (int r = 0; r < RB; r++) {
-                    const int t = r_t[r];
-                    const int b = tid + r * TPE;
-                    if (half & 1) {   // P iteration: Va[pvpq] -= B'^-1 P
-                        if (t == PPN_BT_PV || t == PPN_BT_PQ) {
-                            r_va[r] -= row_dot(M1 + r_ip[r] * ld1, e.P(), n1);
-                            sincos(r_va[r], &r_sn[r], &r_cs[r]);
-                            e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
-                        }
-                    } else if (t == PPN_BT_PQ) {   // Q iteration: Vm[pq] -= B''^-1 Q
-                        r_vm[r] -= row_dot(M2 + r_iq[r] * ld2, e.Q(), n2);
-                        e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
-                    }
-                }
-                env_sync<TPE>(mask);
-            }
-            // mismatch: mis = (V conj(Ybus V) - Sbus)/Vm, P over pv+pq, Q over pq; both infinity norms < tol ?
-            bool open = false;
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-                const int t = r_t[r];
-                if (t != PPN_BT_PV && t != PPN_BT_PQ) continue;
-                const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
-                double ir = r_ydr[r] * vr - r_ydi[r] * vi, ii = r_ydr[r] * vi + r_ydi[r] * vr;
-                double jr = 0.0, ji = 0.0;
-#pragma unroll 2
-                for (int q = 0; q < r_deg[r]; q++) {
-                    const int k = r_k0[r] + r_step[r] * q;
-                    const int o = e.eoth()[k];
-                    const double yr = e.eyr()[k], yi = e.eyi()[k];
-                    const double wr = e.vr()[o], wi = e.vi()[o];
-                    if (q & 1) { jr = fma(yr, wr, fma(-yi, wi, jr)); ji = fma(yr, wi, fma(yi, wr, ji)); }
-                    else { ir = fma(yr, wr, fma(-yi, wi, ir)); ii = fma(yr, wi, fma(yi, wr, ii)); }
-                }
-                ir += jr; ii += ji;
-                const double sr = vr * ir + vi * ii, si = vi * ir - vr * ii;   // V conj(I)
-                r_sr[r] = sr; r_si[r] = si;
-                const double rvm = 1.0 / r_vm[r];
-                const double pm = (sr - r_pin[r]) * rvm;
-                e.P()[r_ip[r]] = pm;
-                open |= !(fabs(pm) < cfg.tol);
-                if (t == PPN_BT_PQ) {
-                    const double qm = (si - r_qin[r]) * rvm;
-                    e.Q()[r_iq[r]] = qm;
-                    open |= !(fabs(qm) < cfg.tol);
-                }
-            }
-            const bool any_open = env_any<TPE>(open, mask);
-            env_sync<TPE>(mask);
-            if (!any_open) { success = true; break; }
-            if (half == 2 * cfg.max_it) break;
-            if (half == 0) {
-                gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
-                gj_invert<TPE, MAXR>(M2, n2, ld2, tid, mask);
-            }
-            half++;
-        }
-        n_iter = (half + 1) / 2;
-        // ---- pfsoln: generator Q (and the slack's P) by the thread that owns the generator's bus
-        int n_on = 0;
-        for (int g = tid; g < e.G; g += TPE) n_on += (e.gstat()[g] > 0 && e.btype()[e.gbus()[g]] != PPN_BT_ISOLATED);
-        n_on = env_sum_int<TPE>(n_on, e.redi(), tid, mask);
-#pragma unroll
-        for (int r = 0; r < RB; r++) {
-            const int t = r_t[r];
-            if (t == PPN_BT_ISOLATED) continue;
-            const int b = tid + r * TPE;
-            const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
-            const int g = c.gen_of_sub[s];
-            if (g >= 0 && e.gnode()[g] == node && e.gstat()[g] > 0) {
-                double sr = r_sr[r], si = r_si[r];
-                if (t == PPN_BT_REF) {   // the reference bus is not part of the mismatch vectors
-                    const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
-                    double ir = r_ydr[r] * vr - r_ydi[r] * vi, ii = r_ydr[r] * vi + r_ydi[r] * vr;
-                    for (int q = 0; q < r_deg[r]; q++) {
-                        const int k = r_k0[r] + r_step[r] * q;
-                        const int o = e.eoth()[k];
-                        const double yr = e.eyr()[k], yi = e.eyi()[k];
-                        const double wr = e.vr()[o], wi = e.vi()[o];
-                        ir = fma(yr, wr, fma(-yi, wi, ir));
-                        ii = fma(yr, wi, fma(yi, wr, ii));
-                    }
-                    sr = vr * ir + vi * ii; si = vi * ir - vr * ii;
-                }
-                double pd, qd;
-                bus_demand(e, c, b, pd, qd);
-                double q = si * c.base_mva + qd;
-                if (n_on > 1) {
-                    const double qmin = c.gen_qmin[g], qmax = c.gen_qmax[g];
-                    if (qmin != qmax) q = qmin + ((q - qmin) / (qmax - qmin + 2.220446049250313e-16)) * (qmax - qmin);
-                }
-                e.gqg()[g] = q;
-                if (t == PPN_BT_REF) e.gpg()[g] = sr * c.base_mva + pd;
-            }
-            // adopted bus results: VM = |V|, VA = angle(V) in degrees
-            const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
-            e.vm()[b] = hypot(vr, vi);
-            e.va()[b] = atan2(vi, vr) * (180.0 / PPN_PI);
-        }
-        env_sync<TPE>(mask);   // the branch results below reuse the storage of the mismatch vectors
-        for (int l = tid; l < e.N; l += TPE) {
-            double pf = 0.0, qf = 0.0, pt = 0.0, qt = 0.0;
-            if (e.status()[l]) {
-                const double* y = c.line_y + 8 * l;
-                const int f = e.fbus()[l], t = e.tbus()[l];
-                const double fr = e.vr()[f], fi = e.vi()[f], tr = e.vr()[t], ti = e.vi()[t];
-                const double ifr = y[0] * fr - y[1] * fi + y[2] * tr - y[3] * ti;
-                const double ifi = y[0] * fi + y[1] * fr + y[2] * ti + y[3] * tr;
-                const double itr = y[4] * fr - y[5] * fi + y[6] * tr - y[7] * ti;
-                const double iti = y[4] * fi + y[5] * fr + y[6] * ti + y[7] * tr;
-                pf = (fr * ifr + fi * ifi) * c.base_mva; qf = (fi * ifr - fr * ifi) * c.base_mva;
-                pt = (tr * itr + ti * iti) * c.base_mva; qt = (ti * itr - tr * iti) * c.base_mva;
-            }
-            e.pf()[l] = pf; e.qf()[l] = qf; e.pt()[l] = pt; e.qt()[l] = qt;
-        }
+        double* M1 = args.ws + (size_t)slot * args.ws_stride;
+        success = cfg.dc ? dc_solve<TPE, MAXR, D>(e, c, M1, n1, ld1, ref)
+                         : ac_solve<TPE, MAXR, D, false>(e, c, cfg, M1, M1 + n1 * ld1, n1, n2, ld1, ld2, ref, slot, n_iter);
     }
+    PPN_TICK(11);
     // runpf tail: out-of-service generators report Pg = Qg = 0
     for (int g = tid; g < e.G; g += TPE)
         if (!(e.gstat()[g] > 0 && e.btype()[e.gbus()[g]] != PPN_BT_ISOLATED)) { e.gpg()[g] = 0.0; e.gqg()[g] = 0.0; }
@@ -787,6 +906,10 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
     }
     for (int l = tid; l < e.L; l += TPE) { const double a = e.lpd()[l]; bad |= (a != a) || a > 1e10; }
     const bool any_bad = env_any<TPE>(bad, mask);
+    PPN_TICK(12);
+#ifdef PPN_TIMING
+    if (slot == 0 && tid == 0) ppn_timing_buf[63] = 1;
+#endif
     return !success || any_bad;
 }
 
@@ -1189,6 +1312,14 @@ template <class SD> bool dims_match(const PpnDevCase* c) {
 
 }  // namespace
 
+#ifdef PPN_TIMING
+extern "C" int ppn_debug_timing(long long* out_host, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out_host, ppn_timing_buf, sizeof(long long) * 64);
+    if (reset) { long long z[64] = {0}; cudaMemcpyToSymbol(ppn_timing_buf, z, sizeof(z)); }
+    return (int)e;
+}
+#endif
+
 // -------------------------------------------------------------------------------------------------- launch wrapper
 // tpe: 16 (<= 16 substations), 32 (<= 32 substations) or 256 (one CTA per env, <= 128 substations).  The three IEEE
 // families run kernels specialised on their sizes; any other grid runs the size-generic instantiation.
@@ -1202,7 +1333,7 @@ extern "C" int ppn_launch_step(const PpnDevCase* c, const PpnDevChronics* ch, co
             return launch_group<16, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 32:
             // IEEE-14: 14 two-env CTAs per SM = 28 envs/SM, so that 4096 envs are one wave on 148 SMs
-            if (dims_match<Dims14>(c)) return launch_group<32, 2, Dims14, 14>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+            if (dims_match<Dims14>(c)) return launch_group<32, 2, Dims14, 10>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
             if (dims_match<Dims30>(c)) return launch_group<32, 2, Dims30, 5>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
             return launch_group<32, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 256:
