@@ -116,7 +116,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -251,7 +251,6 @@ def run_b200(args):
         dist.barrier()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if sampler else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -287,6 +286,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t.item())
+    clocks = sampler.stop() if sampler else None      # sampled over the timed, back-to-back and end-to-end loops
     h2d = B * case.action_length
     d2h = B * (case.obs_dynamic_length * 8 + 5 * 8 + 1 + 4)
 
