@@ -151,7 +151,12 @@ int ppn_process_game_over(ppn_env* env, const uint8_t* mask_dev, double* obs_dev
 /* Game.is_action_valid (game.py:755-760): valid_dev uint8 [n_envs]. */
 int ppn_action_valid(ppn_env* env, const uint8_t* act_dev, uint8_t* valid_dev, void* stream);
 
-/* Host-buffer form of ppn_step: copies act_host to the GPU, steps, copies results back and synchronises. */
+/* Host-buffer form of ppn_step (what a host-side agent calls, RunEnv.step semantics, environment.py:848-866): the batch
+ * is cut into chunks, each chunk runs  actions H2D -> step kernel -> results D2H  on its own stream so that copies overlap
+ * the kernels of the other chunks; returns when every result is in the host buffers.  Page-locked buffers
+ * (cudaMallocHost / cudaHostRegister / torch pin_memory) are used in place, pageable ones are staged.  act_host NULL =
+ * do-nothing; obs_host NULL = no observation.  Without auto_reset the observation rows of envs that ended stay untouched
+ * (the reference returns None).  Work enqueued earlier through the device-pointer calls is synchronised first. */
 int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_host, int64_t obs_stride, double* reward_host,
                   uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset);
 

@@ -26,6 +26,7 @@ struct ppn_env {
     PpnDevCfg dcfg{};
     PpnDevState st{};
     bool chronics_loaded = false, initialised = false;
+    bool async_pending = false;   // work was enqueued on a caller stream since the last host-buffer call
     int tpe = 32, envs_per_block = 4, env_smem_bytes = 0, mat_cap = 0;
     double* ws = nullptr;
     long long ws_stride = 0, ws_rows = 0;
@@ -44,6 +45,11 @@ struct ppn_env {
     uint8_t* h_ill = nullptr; uint8_t* d_ill = nullptr;
     int32_t* d_init = nullptr;   // [2B] chronic idx | row0
     cudaStream_t own_stream = nullptr;
+    // host-buffer entry point: the batch is cut into chunks, each with its own stream, so that the copies of one chunk
+    // overlap the kernels of the others
+    static const int MAX_CHUNKS = 16;
+    int n_chunks = 0;
+    cudaStream_t chunk_stream[MAX_CHUNKS] = {};
     std::string err;
 };
 
@@ -222,7 +228,10 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     int cap_bytes = max_smem / env->envs_per_block - fixed - 64;
     if (cap_bytes < 0) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "grid too large for the shared-memory plan"); }
     int cap = cap_bytes / 8;
-    if (tpe <= 32) { if (cap > want) cap = want; }          // small grids: keep occupancy, spill rare big systems to HBM
+    if (tpe <= 32) {                                        // small grids: keep occupancy, spill rare big systems to HBM
+        if (want < env->OBSD) want = env->OBSD;             // the area also stages the observation row (write_observation)
+        if (cap > want) cap = want;
+    }
     else if (cap > worst) cap = worst;                       // one env per CTA: take what the SM has
     cap &= ~1;
     env->mat_cap = cap;
@@ -265,6 +274,7 @@ extern "C" void ppn_destroy(ppn_env* env) {
     void* dev[] = {env->d_act, env->d_obs, env->d_reward, env->d_done, env->d_flag, env->d_ill};
     for (void* p : dev) if (p) cudaFree(p);
     if (env->own_stream) cudaStreamDestroy(env->own_stream);
+    for (int i = 0; i < env->n_chunks; i++) if (env->chunk_stream[i]) cudaStreamDestroy(env->chunk_stream[i]);
     delete env;
 }
 
@@ -329,7 +339,11 @@ extern "C" int ppn_load_chronics(ppn_env* env, int n_chronics, const ppn_chronic
 
 static int launch(ppn_env* env, PpnStepArgs& a, cudaStream_t s) {
     a.ws = env->ws; a.ws_stride = env->ws_stride; a.mat_cap = env->mat_cap; a.stats = env->stats;
-    a.n_envs = env->B;
+    if (a.n_envs <= 0) { a.n_envs = env->B; a.env_off = 0; }   // whole batch unless the caller set a chunk
+    {   // observation rows as TMA bulk stores when every row starts on a 16-byte boundary
+        static const int no_bulk = getenv("PPN_NO_BULK") != nullptr;
+        a.obs_bulk = !no_bulk && a.obs && (reinterpret_cast<size_t>(a.obs) & 15) == 0 && (a.obs_stride & 1) == 0;
+    }
     if (a.n_cand <= 0) a.n_cand = 1;
     if (a.mode == PPN_MODE_SIMULATE && a.n_cand > 1) {
         // every candidate needs its own spill slice
@@ -344,6 +358,7 @@ static int launch(ppn_env* env, PpnStepArgs& a, cudaStream_t s) {
     }
     int rc = ppn_launch_step(&env->dc, &env->dch, &env->dcfg, &env->st, &a, env->tpe, env->envs_per_block, env->env_smem_bytes, s);
     env->launches++;
+    env->async_pending = true;
     if (rc != 0) return fail(env, PPN_E_CUDA, std::string("step kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
     return PPN_OK;
 }
@@ -452,8 +467,9 @@ extern "C" int ppn_action_valid(ppn_env* env, const uint8_t* act_dev, uint8_t* v
 }
 
 static int ensure_staging(ppn_env* env) {
-    if (env->h_act) return PPN_OK;
+    if (env->d_act) return PPN_OK;
     const size_t B = env->B;
+    const size_t iw = 1 + 2 * env->N + env->S;
     CK(cudaMallocHost(&env->h_act, B * env->A));
     CK(cudaMalloc(&env->d_act, B * env->A));
     CK(cudaMallocHost(&env->h_obs, B * env->OBSD * sizeof(double)));
@@ -464,12 +480,31 @@ static int ensure_staging(ppn_env* env) {
     CK(cudaMalloc(&env->d_done, B));
     CK(cudaMallocHost(&env->h_flag, B * sizeof(int32_t)));
     CK(cudaMalloc(&env->d_flag, B * sizeof(int32_t)));
-    const size_t iw = 1 + 2 * env->N + env->S;
     CK(cudaMallocHost(&env->h_ill, B * iw));
     CK(cudaMalloc(&env->d_ill, B * iw));
+    // two chunks measured best on B200 (every chunk ends with its own slowest env, so more chunks overlap no more copy
+    // time and only add launches); PPN_HOST_CHUNKS overrides the count
+    int n = B >= 1024 ? 2 : 1;
+    if (const char* v = getenv("PPN_HOST_CHUNKS")) n = atoi(v);
+    if (n < 1) n = 1;
+    if (n > ppn_env::MAX_CHUNKS) n = ppn_env::MAX_CHUNKS;
+    if (n > (int)B) n = (int)B;
+    for (int i = 0; i < n; i++) CK(cudaStreamCreateWithFlags(&env->chunk_stream[i], cudaStreamNonBlocking));
+    env->n_chunks = n;
     return PPN_OK;
 }
 
+// true when p is page-locked host memory the copy engines can reach directly (cudaMallocHost / cudaHostRegister)
+static bool is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// RunEnv.step with HOST buffers.  The batch is cut into chunks; chunk i runs  actions H2D -> step kernel -> results D2H
+// on its own stream, so the copies of the chunks that finished overlap the kernels of those still running.  Page-locked
+// caller buffers are used in place; pageable ones go through the handle's pinned staging buffers.
 extern "C" int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_host, int64_t obs_stride, double* reward_host,
                              uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset) {
     int rc = check_ready(env, "ppn_step_host");
@@ -478,34 +513,83 @@ extern "C" int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_
     CK(cudaSetDevice(env->device));
     rc = ensure_staging(env);
     if (rc) return rc;
-    cudaStream_t s = env->own_stream;
-    const size_t B = env->B, iw = 1 + 2 * env->N + env->S;
-    if (act_host) {
-        memcpy(env->h_act, act_host, B * env->A);
-        CK(cudaMemcpyAsync(env->d_act, env->h_act, B * env->A, cudaMemcpyHostToDevice, s));
+    // the chunk streams do not order with the caller's streams: finish what device-pointer calls enqueued
+    if (env->async_pending) CK(cudaDeviceSynchronize());
+    const size_t B = env->B, iw = 1 + 2 * env->N + env->S, A = env->A, OD = env->OBSD;
+    const bool act_direct = is_pinned(act_host);
+    // ---- zero-copy: every output buffer is page-locked, so the step kernel writes its results straight into them over
+    // PCIe as each env finishes (the transfer overlaps the envs that are still iterating); one launch, no D2H copies.
+    {
+        void* outs[5] = {obs_host, reward_host, done_host, flag_host, illegal_host};
+        void* dev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        bool direct = getenv("PPN_HOST_STAGED") == nullptr;
+        for (int i = 0; i < 5 && direct; i++) {
+            if (!outs[i]) continue;
+            if (!is_pinned(outs[i]) || cudaHostGetDevicePointer(&dev[i], outs[i], 0) != cudaSuccess) { cudaGetLastError(); direct = false; }
+        }
+        if (direct) {
+            cudaStream_t s = env->own_stream;
+            if (act_host) {
+                if (!act_direct) memcpy(env->h_act, act_host, B * A);
+                CK(cudaMemcpyAsync(env->d_act, act_direct ? act_host : env->h_act, B * A, cudaMemcpyHostToDevice, s));
+            }
+            PpnStepArgs a{};
+            a.mode = PPN_MODE_STEP; a.auto_reset = auto_reset; a.act = act_host ? env->d_act : nullptr;
+            a.obs = (double*)dev[0]; a.obs_stride = obs_stride; a.reward = (double*)dev[1]; a.done = (uint8_t*)dev[2];
+            a.flag = (int32_t*)dev[3]; a.illegal = (uint8_t*)dev[4];
+            rc = launch(env, a, s);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(s));
+            env->async_pending = false;
+            return PPN_OK;
+        }
     }
-    PpnStepArgs a{};
-    a.mode = PPN_MODE_STEP; a.auto_reset = auto_reset; a.act = act_host ? env->d_act : nullptr;
-    a.obs = obs_host ? env->d_obs : nullptr; a.obs_stride = env->OBSD;
-    a.reward = env->d_reward; a.done = env->d_done; a.flag = env->d_flag; a.illegal = illegal_host ? env->d_ill : nullptr;
-    rc = launch(env, a, s);
-    if (rc) return rc;
-    if (obs_host) CK(cudaMemcpyAsync(env->h_obs, env->d_obs, B * env->OBSD * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(env->h_reward, env->d_reward, B * 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(env->h_done, env->d_done, B, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(env->h_flag, env->d_flag, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (illegal_host) CK(cudaMemcpyAsync(env->h_ill, env->d_ill, B * iw, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (obs_host) {
-        // rows of envs that ended (and were not auto-reset) hold no observation: leave the caller's row untouched
+    // ---- staged / chunked copies.  Rows of envs that ended without auto-reset hold no observation and must stay
+    // untouched, which a plain copy cannot do: those go through the staging buffer.
+    const bool obs_direct = obs_host && auto_reset && is_pinned(obs_host);
+    const bool rew_direct = is_pinned(reward_host), done_direct = is_pinned(done_host), flag_direct = is_pinned(flag_host),
+               ill_direct = is_pinned(illegal_host);
+    if (act_host && !act_direct) memcpy(env->h_act, act_host, B * A);
+    const int nc = env->n_chunks;
+    for (int k = 0; k < nc; k++) {
+        const size_t e0 = B * k / nc, e1 = B * (k + 1) / nc, n = e1 - e0;
+        if (n == 0) continue;
+        cudaStream_t s = env->chunk_stream[k];
+        if (act_host)
+            CK(cudaMemcpyAsync(env->d_act + e0 * A, (act_direct ? act_host : env->h_act) + e0 * A, n * A, cudaMemcpyHostToDevice, s));
+        PpnStepArgs a{};
+        a.mode = PPN_MODE_STEP; a.auto_reset = auto_reset; a.n_envs = (int)n; a.env_off = (int)e0;
+        a.act = act_host ? env->d_act + e0 * A : nullptr;
+        a.obs = obs_host ? env->d_obs + e0 * OD : nullptr; a.obs_stride = OD;
+        a.reward = env->d_reward + e0 * 5; a.done = env->d_done + e0; a.flag = env->d_flag + e0;
+        a.illegal = illegal_host ? env->d_ill + e0 * iw : nullptr;
+        rc = launch(env, a, s);
+        if (rc) return rc;
+        if (obs_host) {
+            if (obs_direct)
+                CK(cudaMemcpy2DAsync(obs_host + e0 * obs_stride, obs_stride * sizeof(double), env->d_obs + e0 * OD, OD * sizeof(double),
+                                     OD * sizeof(double), n, cudaMemcpyDeviceToHost, s));
+            else
+                CK(cudaMemcpyAsync(env->h_obs + e0 * OD, env->d_obs + e0 * OD, n * OD * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaMemcpyAsync((rew_direct ? reward_host : env->h_reward) + e0 * 5, env->d_reward + e0 * 5, n * 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync((done_direct ? done_host : env->h_done) + e0, env->d_done + e0, n, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync((flag_direct ? flag_host : env->h_flag) + e0, env->d_flag + e0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (illegal_host)
+            CK(cudaMemcpyAsync((ill_direct ? illegal_host : env->h_ill) + e0 * iw, env->d_ill + e0 * iw, n * iw, cudaMemcpyDeviceToHost, s));
+    }
+    for (int k = 0; k < nc; k++) CK(cudaStreamSynchronize(env->chunk_stream[k]));
+    env->async_pending = false;
+    if (done_host && !done_direct) memcpy(done_host, env->h_done, B);
+    if (obs_host && !obs_direct) {
+        const uint8_t* dn = done_direct ? done_host : env->h_done;
         for (size_t e = 0; e < B; e++)
-            if (auto_reset || !env->h_done[e])
-                memcpy(obs_host + e * obs_stride, env->h_obs + e * env->OBSD, env->OBSD * sizeof(double));
+            if (auto_reset || !dn[e])
+                memcpy(obs_host + e * obs_stride, env->h_obs + e * OD, OD * sizeof(double));
     }
-    if (reward_host) memcpy(reward_host, env->h_reward, B * 5 * sizeof(double));
-    if (done_host) memcpy(done_host, env->h_done, B);
-    if (flag_host) memcpy(flag_host, env->h_flag, B * sizeof(int32_t));
-    if (illegal_host) memcpy(illegal_host, env->h_ill, B * iw);
+    if (reward_host && !rew_direct) memcpy(reward_host, env->h_reward, B * 5 * sizeof(double));
+    if (flag_host && !flag_direct) memcpy(flag_host, env->h_flag, B * sizeof(int32_t));
+    if (illegal_host && !ill_direct) memcpy(illegal_host, env->h_ill, B * iw);
     return PPN_OK;
 }
 

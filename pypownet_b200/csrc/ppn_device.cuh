@@ -91,7 +91,9 @@ struct PpnDevState {
 
 struct PpnStepArgs {
     int mode;
-    int n_envs;
+    int n_envs;                 // envs of this launch
+    int env_off;                // first env of this launch (chunked launches of the host-buffer entry point); the
+                                // output pointers below are already offset to its first row
     int n_cand;                 // simulate: candidates per env (else 1)
     int auto_reset;
     const uint8_t* act;         // [n_envs*n_cand][A] or NULL (do-nothing)
@@ -100,6 +102,7 @@ struct PpnStepArgs {
     const int32_t* init_row0;     // PPN_MODE_INIT: [n_envs] or NULL
     double* obs;                // [rows][obs_stride] or NULL
     long long obs_stride;
+    int obs_bulk;               // 1: rows leave through one TMA bulk store each (16-byte aligned rows)
     double* reward;             // [rows][5] or NULL
     uint8_t* done;              // [rows] or NULL
     int32_t* flag;              // [rows] or NULL

@@ -18,6 +18,7 @@
 // Gauss-Jordan inverse of B' and B'' (symmetric, positive definite for connected grids without phase shifters).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include "ppn_device.cuh"
 
 #define PPN_FULL 0xffffffffu
@@ -97,9 +98,11 @@ template <int TPE> __device__ __forceinline__ double env_sum_double(double v, do
 // run-time for any other grid.
 template <int S_, int G_, int L_, int N_> struct StaticDims {
     static constexpr int S = S_, G = G_, L = L_, N = N_, NB = 2 * S_, A = G_ + L_ + 3 * N_;
+    static constexpr int NB_MAX = 2 * S_;   // compile-time bound on the buses of an env
     __device__ __forceinline__ void init_dims(const PpnDevCase&) {}
 };
 struct DynDims {
+    static constexpr int NB_MAX = 0;        // unknown at compile time
     int S, G, L, N, NB, A;
     __device__ __forceinline__ void init_dims(const PpnDevCase& c) { S = c.S; G = c.G; L = c.L; N = c.N; NB = c.NB; A = c.A; }
 };
@@ -559,8 +562,8 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
     // unit phasor, injections, Ybus diagonal and list position stay in registers for the whole iteration; only
     // the rectangular voltages (read by neighbours) and the mismatch vectors (read by the solves) go through
     // shared memory.
-    constexpr int RB = TPE <= 32 ? 2 : 1;
-    double r_vm[RB], r_va[RB], r_cs[RB], r_sn[RB], r_pin[RB], r_qin[RB], r_ydr[RB], r_ydi[RB], r_sr[RB], r_si[RB];
+    constexpr int RB = TPE > 32 ? 1 : (D::NB_MAX > 0 ? (D::NB_MAX + TPE - 1) / TPE : 2);
+    double r_vm[RB], r_rvm[RB], r_va[RB], r_cs[RB], r_sn[RB], r_pin[RB], r_qin[RB], r_ydr[RB], r_ydi[RB], r_sr[RB], r_si[RB];
     int r_t[RB], r_ip[RB], r_iq[RB], r_deg[RB], r_k0[RB], r_step[RB];
     PPN_TICK(4);
     // V0 from the stored state; on-line generators impose their set-point magnitude
@@ -569,7 +572,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         const int b = tid + r * TPE;
         const int t = b < NB ? e.btype()[b] : PPN_BT_ISOLATED;
         r_t[r] = t;
-        r_vm[r] = 1.0; r_va[r] = 0.0; r_cs[r] = 1.0; r_sn[r] = 0.0; r_pin[r] = 0.0; r_qin[r] = 0.0;
+        r_vm[r] = 1.0; r_rvm[r] = 1.0; r_va[r] = 0.0; r_cs[r] = 1.0; r_sn[r] = 0.0; r_pin[r] = 0.0; r_qin[r] = 0.0;
         r_ydr[r] = 0.0; r_ydi[r] = 0.0; r_sr[r] = 0.0; r_si[r] = 0.0;
         r_ip[r] = 0; r_iq[r] = 0; r_deg[r] = 0; r_k0[r] = 0; r_step[r] = 1;
         if (t == PPN_BT_ISOLATED) continue;
@@ -585,6 +588,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         e.vr()[b] = vr; e.vi()[b] = vi;
         const double vm = hypot(vr, vi);   // fdpf: Vm = abs(V0), Va = angle(V0)
         r_vm[r] = vm;
+        r_rvm[r] = 1.0 / vm;
         r_va[r] = atan2(vi, vr);           // radians
         r_cs[r] = vr / vm; r_sn[r] = vi / vm;
         r_pin[r] = e.pin()[b]; r_qin[r] = e.qin()[b];
@@ -645,6 +649,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                     }
                 } else if (t == PPN_BT_PQ) {   // Q iteration: Vm[pq] -= B''^-1 Q
                     r_vm[r] -= row_dot(M2 + r_iq[r] * ld2, e.Q(), n2);
+                    r_rvm[r] = 1.0 / r_vm[r];
                     e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
                 }
             }
@@ -675,7 +680,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
             ir += jr; ii += ji;
             const double sr = vr * ir + vi * ii, si = vi * ir - vr * ii;   // V conj(I)
             r_sr[r] = sr; r_si[r] = si;
-            const double rvm = 1.0 / r_vm[r];
+            const double rvm = r_rvm[r];   // 1/Vm only changes in the Q half-iterations
             const double pm = (sr - r_pin[r]) * rvm;
             e.P()[r_ip[r]] = pm;
             open |= !(fabs(pm) < cfg.tol);
@@ -982,14 +987,18 @@ __device__ __forceinline__ void reset_grid(Env<TPE, D>& e, const PpnDevCase& c) 
     env_sync<TPE>(e.mask);
 }
 
-// Dynamic prefix of Observation.as_array (environment.py:451-466, 511-517), 7L+7G+13N+S+6 values.
+// Dynamic prefix of Observation.as_array (environment.py:451-466, 511-517), 7L+7G+13N+S+6 values.  The row is
+// assembled in shared memory (`stage`: the matrix area, free once the cascade is over) and leaves in one linear,
+// fully coalesced sweep -- `out` may be device memory or page-locked host memory written over PCIe (ppn_step_host).
+// stage == nullptr: the fields are written to `out` directly.
 template <int TPE, class D>
-__device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevChronics& ch, double* out) {
+__device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevChronics& ch, double* out,
+                                                  double* stage, bool bulk) {
     const int G = e.G, L = e.L, N = e.N, S = e.S, tid = e.tid;
     compute_isolated(e);
     const float* row = chronic_row(ch, e.cursor()[0], max(e.cursor()[1], 0));   // maintenance horizon, date
     const float* prow = chronic_row(ch, e.misc()[6], e.misc()[7]);               // planned injections
-    double* o = out;
+    double* o = stage ? stage : out;
     for (int l = tid; l < L; l += TPE) {
         o[l] = e.lpd()[l];
         o[L + l] = e.mark()[e.lbus()[l]] ? 1.0 : 0.0;
@@ -1040,6 +1049,27 @@ __device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCa
         o[4 * N + l] = e.qt()[l];
         o[5 * N + l] = e.vm()[e.tbus()[l]];
     }
+    if (stage) {
+        const int n = 7 * L + 7 * G + 13 * N + S + 6;
+        const int nb = n & ~1;                      // bulk copies move multiples of 16 bytes
+        if (bulk && (reinterpret_cast<size_t>(out) & 15) == 0) {
+            // one TMA bulk store per row (cp.async.bulk shared -> global): full-width write transactions, which is
+            // what makes page-locked host memory behind PCIe a usable destination, and no store loop for the warp
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the async proxy
+            env_sync<TPE>(e.mask);
+            if (tid == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(out), "r"(saddr(stage)), "r"(nb * 8) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (nb < n) out[nb] = stage[nb];
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the source may be reused / freed
+            }
+            env_sync<TPE>(e.mask);
+        } else {
+            env_sync<TPE>(e.mask);
+            for (int i = tid; i < n; i += TPE) out[i] = stage[i];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------ the kernel
@@ -1052,7 +1082,7 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
     const int slot = blockIdx.x * envs_per_block + local;          // output row
     const int n_rows_out = args.n_envs * args.n_cand;
     if (slot >= n_rows_out) return;
-    const int env = slot / args.n_cand;
+    const int env = args.env_off + slot / args.n_cand;   // state row; `slot` is the output row of this launch
     Env<TPE, D> e;
     e.init_dims(c);
     e.tid = TPE <= 32 ? (threadIdx.x & (TPE - 1)) : threadIdx.x;
@@ -1193,7 +1223,7 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
         refresh_element_buses(e, c);
         load_next_timestep(e, c, ch, cfg, is_sim && !reset_pass, env);
         int d2 = 0;
-        const bool div = cascade<TPE, MAXR, D>(e, c, cfg, args, slot, n_lf, n_it, d2);
+        const bool div = cascade<TPE, MAXR, D>(e, c, cfg, args, args.env_off * args.n_cand + slot, n_lf, n_it, d2);   // global row: spill slice
         if (reset_pass) {
             if (!div || ++attempts >= cfg.max_reset_attempts) { done = false; break; }
             continue;
@@ -1257,7 +1287,7 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
     // ---- outputs
     if (args.obs && !done) {
         flows_ampere(e, c);
-        write_observation(e, c, ch, args.obs + (size_t)slot * args.obs_stride);
+        write_observation(e, c, ch, args.obs + (size_t)slot * args.obs_stride, args.mat_cap >= c.OBSD ? e.mat() : nullptr, args.obs_bulk != 0);
     }
     if (!is_sim) {
         env_sync<TPE>(mask);
@@ -1333,7 +1363,12 @@ extern "C" int ppn_launch_step(const PpnDevCase* c, const PpnDevChronics* ch, co
             return launch_group<16, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 32:
             // IEEE-14: 14 two-env CTAs per SM = 28 envs/SM, so that 4096 envs are one wave on 148 SMs
-            if (dims_match<Dims14>(c)) return launch_group<32, 2, Dims14, 10>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+            if (dims_match<Dims14>(c)) {
+                static const int variant = getenv("PPN_VARIANT") ? atoi(getenv("PPN_VARIANT")) : 0;
+                if (variant == 1) return launch_group<32, 2, Dims14, 12>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+                if (variant == 2) return launch_group<32, 2, Dims14, 14>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+                return launch_group<32, 2, Dims14, 10>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+            }
             if (dims_match<Dims30>(c)) return launch_group<32, 2, Dims30, 5>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
             return launch_group<32, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 256:

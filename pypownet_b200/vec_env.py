@@ -200,27 +200,23 @@ class VecRunEnv(object):
         return obs_out, reward, done, flag
 
     def step_pinned(self, actions_pinned, auto_reset=True):
-        """End-to-end step for a host-side agent: actions in pinned host memory -> GPU, step, observation / reward /
-        done / flag back into pinned host tensors, synchronised.  Returns the four pinned tensors (reused per call)."""
+        """End-to-end step for a host-side agent through ppn_step_host: actions in pinned host memory (uint8
+        [B, action_length] tensor, None = do-nothing) -> GPU, step, dynamic observation / reward / done / flag back into
+        pinned host tensors (reused per call), chunked so that copies overlap the kernels.  Synchronous."""
         if not hasattr(self, '_pin'):
             B = self.n_envs
-            self._pin = (torch.empty((B, self.obs_dynamic_length), dtype=torch.float64).pin_memory(),
+            stride = (self.obs_dynamic_length + 1) & ~1      # 16-byte aligned rows: one TMA bulk store per row
+            self._pin_obs_full = torch.empty((B, stride), dtype=torch.float64).pin_memory()
+            self._pin = (self._pin_obs_full[:, :self.obs_dynamic_length],
                          torch.empty((B, 5), dtype=torch.float64).pin_memory(),
                          torch.empty((B,), dtype=torch.uint8).pin_memory(),
                          torch.empty((B,), dtype=torch.int32).pin_memory())
-            self._act_dev = torch.empty((B, self.action_length), dtype=torch.uint8, device=self.device)
-            self._obs_dyn = torch.empty((B, self.obs_dynamic_length), dtype=torch.float64, device=self.device)
         po, pr, pd, pf = self._pin
-        self._act_dev.copy_(actions_pinned, non_blocking=True)
-        with torch.cuda.device(self.device):
-            self._check(self.lib.ppn_step(self.handle, _ptr(self._act_dev), _ptr(self._obs_dyn),
-                                          self.obs_dynamic_length, _ptr(self.reward), _ptr(self.done), _ptr(self.flag),
-                                          None, 1 if auto_reset else 0, self._stream()))
-        po.copy_(self._obs_dyn, non_blocking=True)
-        pr.copy_(self.reward, non_blocking=True)
-        pd.copy_(self.done, non_blocking=True)
-        pf.copy_(self.flag, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if actions_pinned is not None and (actions_pinned.dtype != torch.uint8 or not actions_pinned.is_contiguous()
+                                           or tuple(actions_pinned.shape) != (self.n_envs, self.action_length)):
+            raise ValueError('Expected a contiguous uint8 tensor of shape (%d, %d)' % (self.n_envs, self.action_length))
+        self._check(self.lib.ppn_step_host(self.handle, _ptr(actions_pinned), _ptr(po), self._pin_obs_full.shape[1],
+                                           _ptr(pr), _ptr(pd), _ptr(pf), None, 1 if auto_reset else 0))
         return po, pr, pd, pf
 
     # ------------------------------------------------------------------------------------------------------------

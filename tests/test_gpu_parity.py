@@ -113,6 +113,46 @@ def test_step_host_matches_device_entry_point():
         assert np.array_equal(f1.cpu().numpy(), f2)
 
 
+@pytest.mark.parametrize('pinned', [True, False])
+def test_chunked_host_entry_point_is_bit_identical(pinned):
+    """ppn_step_host: page-locked result buffers are written by the kernel itself (zero-copy, one launch); pageable ones
+    are staged with the batch cut into chunks on separate streams (copies overlap kernels).  Same bits either way as
+    one device-pointer launch over the whole batch."""
+    fx = Fixture('d14_ac_random')
+    B = 2100
+    rng = np.random.default_rng(5)
+    nch = len(fx.chronics)
+    start_c = rng.integers(0, nch, size=B).astype(np.int32)
+    start_r = np.array([rng.integers(0, fx.chronics[c].n_rows - 1) for c in start_c], dtype=np.int32)
+    e1 = vec_env(fx, B, start_chronics=start_c, start_rows=start_r)
+    e2 = vec_env(fx, B, start_chronics=start_c, start_rows=start_r)
+    case = fx.case
+    nd = case.obs_dynamic_length
+    act = torch.zeros((B, case.action_length), dtype=torch.uint8)
+    if pinned:
+        act = act.pin_memory()
+    obs_h = np.zeros((B, nd + 3))                       # a row stride wider than the dynamic observation
+    for t in range(12):
+        a = np.zeros((B, case.action_length), dtype=np.uint8)
+        rows = rng.integers(0, B, size=B // 4)
+        a[rows, case.n_gen + case.n_load + 2 * case.n_line + rng.integers(case.n_line, size=len(rows))] = 1
+        act.copy_(torch.from_numpy(a))
+        o1, r1, d1, f1 = e1.step(a, auto_reset=True)
+        if pinned:
+            po, pr, pd, pf = e2.step_pinned(act, auto_reset=True)
+            o2, r2, d2, f2 = po.numpy(), pr.numpy(), pd.numpy(), pf.numpy()
+        else:
+            _, r2, d2, f2 = e2.step_host(a, obs_out=obs_h, auto_reset=True)
+            o2 = obs_h[:, :nd]
+        assert np.array_equal(o1.cpu().numpy()[:, :nd], o2), t
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy(), d2)
+        assert np.array_equal(f1.cpu().numpy(), f2)
+    if not pinned:
+        assert e2.counters()['kernel_launches'] > e1.counters()['kernel_launches']   # one launch per chunk
+    else:
+        assert e2.counters()['kernel_launches'] == e1.counters()['kernel_launches']  # zero-copy: one launch
+
+
 def test_is_action_valid_and_illegal_masks():
     fx = Fixture('d14_ac_random')
     env = vec_env(fx, 2)
