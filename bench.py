@@ -182,8 +182,10 @@ def run_reference(args):
 
 
 def workload_config(args, extra):
-    cfg = {'workload': '%s AC, %d batched envs per GPU, do-nothing agent, auto-restart on game over '
-                       '(BASELINE.json configs[1] shape)' % (GRIDS[args.grid], args.envs),
+    cfg = {'workload': '%s AC, %d batched envs per GPU, %s agent, auto-restart on game over '
+                       '(BASELINE.json configs[1] shape)' % (GRIDS[args.grid], args.envs,
+                                                            'do-nothing' if args.agent == 'nothing' else
+                                                            'random node-split + line-switch'),
            'grid': args.grid, 'envs_per_gpu': args.envs, 'chronics': '%d synthetic x %d rows' % (N_CHRONICS, N_ROWS),
            'solver': 'fast-decoupled XB, tol 1e-6, <=25 it (the reference\'s PF_ALG=2)',
            'l2': 'flushed between timed steps (256 MiB write)', 'parallelism': 'env-sharded, dp%d' % args.gpus}
@@ -215,13 +217,32 @@ def run_b200(args):
     env = VecRunEnv(case, cfg, chronics, B, device=local, reward_constant=float(case.n_sub), thermal_limits=imaps,
                     start_chronics=sc, start_rows=sr)
     actions = torch.zeros((B, case.action_length), dtype=torch.uint8, device=dev)      # do-nothing agent
+    action_bank = None
+    if args.agent == 'random':
+        # RandomNodeSplitting + RandomLineSwitch (agent.py:78-158): per env and step one
+        # substation with its element bits i.i.d. Bernoulli(1/2) plus one line switch; 16 pre-drawn batches, cycled
+        rng = np.random.default_rng(1234 + rank)
+        elem_sub = np.asarray(case.elem_sub)
+        bank = np.zeros((16, B, case.action_length), dtype=np.uint8)
+        nt_ = len(elem_sub)
+        for k in range(16):
+            subs = rng.integers(0, case.n_sub, size=B)
+            bits = rng.integers(0, 2, size=(B, nt_), dtype=np.uint8)
+            bank[k, :, :nt_] = bits * (elem_sub[None, :] == subs[:, None])
+            bank[k, np.arange(B), nt_ + rng.integers(0, case.n_line, size=B)] = 1
+        action_bank = torch.from_numpy(bank).to(dev)
+    step_counter = [0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     from pypownet_b200 import sharding
     pack = torch.zeros((B, sharding.PACK_WIDTH), dtype=torch.float64, device=dev)
     gathered = torch.zeros((world * B, sharding.PACK_WIDTH), dtype=torch.float64, device=dev) if world > 1 else None
 
     def one_step():
-        obs, reward, done, flag = env.step(actions, auto_reset=True)
+        a = actions
+        if action_bank is not None:
+            a = action_bank[step_counter[0] % 16]
+            step_counter[0] += 1
+        obs, reward, done, flag = env.step(a, auto_reset=True)
         if world > 1:      # rewards / dones / flags of every shard on every rank (NCCL over NVLink)
             sharding.gather_results(sharding.pack_results(reward, done, flag, out=pack), world, out=gathered)
         return done
@@ -347,6 +368,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--grid', default='case14', choices=sorted(GRIDS))
     ap.add_argument('--envs', type=int, default=4096, help='envs per GPU')
+    ap.add_argument('--agent', default='nothing', choices=['nothing', 'random'],
+                    help="'random': one random node-splitting + one line switch per env and step (BASELINE configs[4])")
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

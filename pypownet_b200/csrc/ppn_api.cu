@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <complex>
+#include <algorithm>
 
 #include "../../include/pypownet_b200.h"
 #include "ppn_device.cuh"
@@ -31,6 +32,13 @@ struct ppn_env {
     double* ws = nullptr;
     long long ws_stride = 0, ws_rows = 0;
     int horizon = 20;
+    int sp_need[2] = {0, 0};   // doubles of factor storage (both matrices) of the U / F sparse structures
+    int sp_blob_dbl[2] = {0, 0};   // doubles of their index tables
+    int sparse = 0;            // solver mode of PpnStepArgs.sparse
+    int alt_sparse = 0, alt_mat_cap = 0, alt_env_smem_bytes = 0;   // plan used once the handle has seen actions
+    int* h_split = nullptr;    // page-locked, mapped: the kernel sets it when an env applies a node switch
+    int* d_split = nullptr;    // its device alias
+    long long ws_dense = 0;
     unsigned long long* stats = nullptr;
     long long launches = 0;
     std::vector<void*> allocs;
@@ -84,6 +92,141 @@ template <typename T> static T* upload(ppn_env* env, const std::vector<T>& v, cu
         dst = upload(env, vec, &_e);                                                                 \
         if (_e != cudaSuccess) return fail(env, PPN_E_CUDA, std::string("upload " #vec ": ") + cudaGetErrorString(_e)); \
     } while (0)
+
+// ---------------------------------------------------------------------------------------- sparse symbolic analysis
+// Minimum-degree order of the substation graph, symbolic LDL^T of the bus-level pattern (U: one row per substation,
+// F: rows 2p, 2p+1 = bus s, s+S of the p-th substation), elimination-tree levels and the static update lists of the
+// left-looking numeric factorisation run by the kernel (ppn_kernels.cu: sp_factor / sp_invert).
+struct SparseHost {
+    int n = 0, nnz = 0, n_lev = 0;
+    std::vector<short> bus_row, rowidx, ecol, parent, row_lev, rowoff;
+    std::vector<int> rpack, rowpk, colpk;
+    std::vector<int> colptr, lev_ptr, lev_ent, trip_ptr, trip, line_pos, rowptr, rowent, lev_rows_ptr, lev_rows;
+};
+
+static std::vector<int> min_degree_order(int S, int N, const int* lor, const int* lex) {
+    std::vector<char> a((size_t)S * S, 0), alive(S, 1);
+    for (int l = 0; l < N; l++) if (lor[l] != lex[l]) { a[(size_t)lor[l] * S + lex[l]] = 1; a[(size_t)lex[l] * S + lor[l]] = 1; }
+    std::vector<int> perm;
+    for (int it = 0; it < S; it++) {
+        int best = -1, bd = 1 << 30;
+        for (int s = 0; s < S; s++) {
+            if (!alive[s]) continue;
+            int d = 0;
+            for (int t = 0; t < S; t++) d += a[(size_t)s * S + t];
+            if (d < bd) { bd = d; best = s; }
+        }
+        perm.push_back(best);
+        alive[best] = 0;
+        std::vector<int> nb;
+        for (int t = 0; t < S; t++) if (a[(size_t)best * S + t] && alive[t]) nb.push_back(t);
+        for (int x : nb) for (int y : nb) if (x != y) a[(size_t)x * S + y] = 1;
+        for (int t = 0; t < S; t++) { a[(size_t)best * S + t] = 0; a[(size_t)t * S + best] = 0; }
+    }
+    return perm;
+}
+
+// `order`: bus of each row (elimination order).  Fills every table of SparseHost; `row_level` gets the level of each row.
+static void build_sparse_ordered(int S, int N, const int* lor, const int* lex, const std::vector<int>& order, bool full, SparseHost& h,
+                                 std::vector<int>& row_level) {
+    const int NB = 2 * S, n = (int)order.size();
+    h = SparseHost();
+    h.n = n;
+    h.bus_row.assign(NB, -1);
+    for (int p = 0; p < n; p++) h.bus_row[order[p]] = (short)p;
+    std::vector<char> a((size_t)n * n, 0);   // lower triangle: a[i*n+j], i > j
+    auto couple = [&](int x, int y) {
+        const int i = h.bus_row[x], j = h.bus_row[y];
+        if (i < 0 || j < 0 || i == j) return;
+        a[(size_t)(i > j ? i : j) * n + (i > j ? j : i)] = 1;
+    };
+    for (int l = 0; l < N; l++)
+        for (int on = 0; on < (full ? 2 : 1); on++)
+            for (int en = 0; en < (full ? 2 : 1); en++) couple(lor[l] + S * on, lex[l] + S * en);
+    h.parent.assign(n, -1);
+    for (int k = 0; k < n; k++) {
+        std::vector<int> st;
+        for (int i = k + 1; i < n; i++) if (a[(size_t)i * n + k]) st.push_back(i);
+        if (!st.empty()) h.parent[k] = (short)st[0];
+        for (size_t x = 0; x < st.size(); x++) for (size_t y = 0; y < x; y++) a[(size_t)st[x] * n + st[y]] = 1;
+    }
+    std::vector<int> pos((size_t)n * n, -1);
+    h.colptr.assign(n + 1, 0);
+    for (int k = 0; k < n; k++) {
+        h.colptr[k] = (int)h.rowidx.size();
+        for (int i = k + 1; i < n; i++)
+            if (a[(size_t)i * n + k]) { pos[(size_t)i * n + k] = (int)h.rowidx.size(); h.rowidx.push_back((short)i); h.ecol.push_back((short)k); }
+    }
+    h.colptr[n] = (int)h.rowidx.size();
+    h.nnz = (int)h.rowidx.size();
+    std::vector<int> lev(n, 0);
+    for (int k = 0; k < n; k++) if (h.parent[k] >= 0 && lev[h.parent[k]] < lev[k] + 1) lev[h.parent[k]] = lev[k] + 1;
+    h.n_lev = 0;
+    for (int k = 0; k < n; k++) if (lev[k] + 1 > h.n_lev) h.n_lev = lev[k] + 1;
+    h.lev_ptr.assign(h.n_lev + 1, 0);
+    for (int v = 0; v < h.n_lev; v++) {
+        h.lev_ptr[v] = (int)h.lev_ent.size();
+        for (int k = 0; k < n; k++) {
+            if (lev[k] != v) continue;
+            h.lev_ent.push_back(h.nnz + k);
+            for (int e = h.colptr[k]; e < h.colptr[k + 1]; e++) h.lev_ent.push_back(e);
+        }
+    }
+    h.lev_ptr[h.n_lev] = (int)h.lev_ent.size();
+    // rows by level and the row-wise view of L (forward substitution gathers along rows)
+    h.lev_rows_ptr.assign(h.n_lev + 1, 0);
+    for (int v = 0; v < h.n_lev; v++) {
+        h.lev_rows_ptr[v] = (int)h.lev_rows.size();
+        for (int k = 0; k < n; k++) if (lev[k] == v) h.lev_rows.push_back(k);
+    }
+    h.lev_rows_ptr[h.n_lev] = (int)h.lev_rows.size();
+    h.rowptr.assign(n + 1, 0);
+    for (int i = 0; i < n; i++) {
+        h.rowptr[i] = (int)h.rowent.size();
+        for (int k = 0; k < i; k++) if (pos[(size_t)i * n + k] >= 0) h.rowent.push_back(pos[(size_t)i * n + k]);
+    }
+    h.rowptr[n] = (int)h.rowent.size();
+    for (int en : h.rowent) h.rpack.push_back(((8 * en) << 16) | (8 * (int)h.ecol[en]));
+    for (int i = 0; i < n; i++) {
+        h.rowpk.push_back((h.rowptr[i] << 8) | (h.rowptr[i + 1] - h.rowptr[i]));
+        h.colpk.push_back((h.colptr[i] << 8) | (h.colptr[i + 1] - h.colptr[i]));
+    }
+    for (int en = 0; en < h.nnz; en++) h.rowoff.push_back((short)(8 * h.rowidx[en]));
+    for (int k = 0; k < n; k++) h.row_lev.push_back((short)lev[k]);
+    row_level = lev;
+    // update terms: target (i,j), i >= j, gets -T(i,k) L(j,k) for every k < j with both entries present
+    h.trip_ptr.assign(h.nnz + n + 1, 0);
+    auto terms = [&](int i, int j) {
+        for (int k = 0; k < j; k++) {
+            const int p1 = pos[(size_t)i * n + k], p2 = pos[(size_t)j * n + k];
+            if (p1 >= 0 && p2 >= 0) h.trip.push_back((p1 << 16) | p2);
+        }
+    };
+    for (int e = 0; e < h.nnz; e++) { h.trip_ptr[e] = (int)h.trip.size(); terms(h.rowidx[e], h.ecol[e]); }
+    for (int k = 0; k < n; k++) { h.trip_ptr[h.nnz + k] = (int)h.trip.size(); terms(k, k); }
+    h.trip_ptr[h.nnz + n] = (int)h.trip.size();
+    for (int l = 0; l < N; l++)
+        for (int on = 0; on < (full ? 2 : 1); on++)
+            for (int en = 0; en < (full ? 2 : 1); en++) {
+                const int i = h.bus_row[lor[l] + S * on], j = h.bus_row[lex[l] + S * en];
+                h.line_pos.push_back(i == j ? -1 : pos[(size_t)(i > j ? i : j) * n + (i > j ? j : i)]);
+            }
+}
+
+// Minimum-degree order first (F: the two buses of a substation next to each other), then the rows are re-sorted by
+// their level in the elimination tree -- still a valid elimination order with the same fill -- so that the rows of
+// one level are contiguous: the level-scheduled solves of the kernel walk plain ranges of rows.
+static void build_sparse(int S, int N, const int* lor, const int* lex, const std::vector<int>& perm, bool full, SparseHost& h) {
+    std::vector<int> order, lev;
+    for (int p = 0; p < S; p++) { order.push_back(perm[p]); if (full) order.push_back(perm[p] + S); }
+    build_sparse_ordered(S, N, lor, lex, order, full, h, lev);
+    std::vector<int> idx(order.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return lev[x] < lev[y]; });
+    std::vector<int> order2(order.size());
+    for (size_t i = 0; i < idx.size(); i++) order2[i] = order[idx[i]];
+    build_sparse_ordered(S, N, lor, lex, order2, full, h, lev);
+}
 
 extern "C" const char* ppn_build_info(void) {
     return "pypownet_b200 step path; sm_100a; fused warp/CTA-per-env fast-decoupled XB + DC load-flow; built " __DATE__;
@@ -175,6 +318,47 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     UP(dp, vg0); c.gen_vg0 = dp; UP(dp, pd0); c.load_pd0 = dp; UP(dp, qd0); c.load_qd0 = dp; UP(dp, thermal); c.thermal = dp;
     UP(up8, status0); c.line_status0 = up8;
 
+    // sparse LDL^T structures (U: un-split grid, F: any bus split)
+    {
+        const std::vector<int> perm = min_degree_order(S, N, lor.data(), lex.data());
+        for (int f = 0; f < 2; f++) {
+            SparseHost h;
+            build_sparse(S, N, lor.data(), lex.data(), perm, f == 1, h);
+            // byte offsets of entries / rows are packed into 16 bits
+            if (h.nnz >= 8192 || 8 * h.n >= 32768) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "ppn_create: grid too large for the sparse factor tables"); }
+            PpnDevSparse& d = c.sp[f];
+            d.n = h.n; d.nnz = h.nnz; d.n_lev = h.n_lev;
+            // hybrid cut: the lowest level from which at most 40 rows remain (at least one level stays sparse when there is one)
+            int cut = h.n_lev > 1 ? 1 : 0;
+            int cut_rows = 28;   // measured best on B200 for IEEE-118 (12 / 20 / 28 / 40 rows: 1.60 / 1.62 / 1.72 / 1.67 M env-steps/s);
+                                 // at most 40: hyb_invert2 keeps a 5 x 5 tile per thread on an 8 x 8 thread grid
+            if (const char* v = getenv("PPN_CUT_ROWS")) { cut_rows = atoi(v); if (cut_rows > 40) cut_rows = 40; if (cut_rows < 1) cut_rows = 1; }
+            while (cut < h.n_lev - 1 && h.n - h.lev_rows_ptr[cut] > cut_rows) cut++;
+            d.cut_lev = cut; d.cut_row = h.lev_rows_ptr[cut]; d.cut_ent = h.colptr[d.cut_row]; d.nt = h.n - d.cut_row;
+            std::vector<int> blob;
+            auto put_i = [&](const std::vector<int>& v) { const int o = (int)blob.size(); blob.insert(blob.end(), v.begin(), v.end()); return o; };
+            auto put_s = [&](const std::vector<short>& v) {
+                const int o = (int)blob.size();
+                blob.resize(o + (v.size() + 1) / 2, 0);
+                if (!v.empty()) memcpy(blob.data() + o, v.data(), v.size() * sizeof(short));
+                return o;
+            };
+            d.o_colptr = put_i(h.colptr); d.o_lev_ptr = put_i(h.lev_ptr); d.o_lev_ent = put_i(h.lev_ent);
+            d.o_trip_ptr = put_i(h.trip_ptr); d.o_trip = put_i(h.trip); d.o_line_pos = put_i(h.line_pos);
+            d.o_rowptr = put_i(h.rowptr); d.o_rowent = put_i(h.rowent);
+            d.o_lev_rows_ptr = put_i(h.lev_rows_ptr); d.o_lev_rows = put_i(h.lev_rows); d.o_rpack = put_i(h.rpack);
+            d.o_rowpk = put_i(h.rowpk); d.o_colpk = put_i(h.colpk);
+            d.o_rowidx = put_s(h.rowidx); d.o_ecol = put_s(h.ecol); d.o_parent = put_s(h.parent); d.o_bus_row = put_s(h.bus_row);
+            d.o_row_lev = put_s(h.row_lev); d.o_rowoff = put_s(h.rowoff);
+            if (blob.size() & 1) blob.push_back(0);
+            d.blob_words = (int)blob.size();
+            int* bp32;
+            UP(bp32, blob); d.blob = bp32;
+            env->sp_need[f] = 2 * ppn_sp_factor_doubles(h.n, h.nnz) + 2 * d.nt * (d.nt | 1);   // + the dense top blocks
+            env->sp_blob_dbl[f] = d.blob_words / 2;
+        }
+    }
+
     // static tail of Observation.as_array (environment.py:583-595)
     {
         std::vector<double>& t = env->obs_static;
@@ -221,21 +405,42 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     // Shared-memory room for B' and B'': the un-split grid (n1 = S-1 buses) with up to two generators off (n2 = PQ
     // buses); larger systems (node splitting, more generators off) use the env's slice of the HBM workspace.
     const int n1 = S - 1, n2 = S - 1 - (G > 3 ? G - 3 : 0);
-    int want = n1 * (n1 | 1) + n2 * (n2 | 1);
-    const int worst = 2 * (NB - 1) * ((NB - 1) | 1);
-    if (want > worst) want = worst;
+    // Linear solver (PpnStepArgs.sparse), chosen per grid size from measurements on B200; PPN_SPARSE overrides:
+    //   0 dense Gauss-Jordan inverses      IEEE-14 sized grids: both inverses by one warp with the rows in registers
+    //   1 sparse LDL^T + explicit inverses warp per env above 16 substations (IEEE-30: +46 % over the dense inverse);
+    //                                      also the CTA-per-env plan once a handle has received topology actions
+    //   3 hybrid sparse / dense top block  CTA per env (IEEE-118): 4.7x the dense 117^3 inverse, two CTAs per SM
+    //   (2 = sparse LDL^T with level-scheduled triangular solves: correct but latency-bound, kept for reference)
+    env->sparse = tpe == 256 ? 3 : (tpe == 32 && S > 16 ? 1 : 0);
+    if (const char* v = getenv("PPN_SPARSE")) env->sparse = atoi(v);
+    env->ws_dense = 2LL * NB * (NB | 1);
+    const int worst = (int)env->ws_dense + env->sp_need[1] + env->sp_blob_dbl[1];
     env->envs_per_block = tpe == 16 ? 4 : (tpe == 32 ? 2 : 1);   // 64-thread CTAs for the sub-warp / warp kernels
-    int cap_bytes = max_smem / env->envs_per_block - fixed - 64;
+    const int cap_bytes = max_smem / env->envs_per_block - fixed - 64;
     if (cap_bytes < 0) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "grid too large for the shared-memory plan"); }
-    int cap = cap_bytes / 8;
-    if (tpe <= 32) {                                        // small grids: keep occupancy, spill rare big systems to HBM
-        if (want < env->OBSD) want = env->OBSD;             // the area also stages the observation row (write_observation)
-        if (cap > want) cap = want;
+    // doubles of shared memory per env for matrices / factors / tables under a given solver mode
+    auto plan = [&](int mode) {
+        int want = n1 * (n1 | 1) + n2 * (n2 | 1);
+        if (mode == 1) want = (n1 + 1) * (n1 | 1) + (n2 + 1) * (n2 | 1) + env->sp_need[0] + env->sp_blob_dbl[0];
+        if (mode >= 2) want = env->sp_need[0] + env->sp_blob_dbl[0];
+        want = (want + 3) & ~1;   // the capacity below is rounded down to an even number of doubles
+        if (want > worst) want = worst;
+        int cap = cap_bytes / 8;
+        if (tpe <= 32 || mode >= 2) {   // keep occupancy: the un-split grid fits, rare bigger systems spill to HBM
+            if (want < env->OBSD) want = env->OBSD;   // the area also stages the observation row (write_observation)
+            if (cap > want) cap = want;
+        } else if (cap > worst) cap = worst;           // one env per CTA: take what the SM has
+        return cap & ~1;
+    };
+    env->mat_cap = plan(env->sparse);
+    env->env_smem_bytes = fixed + env->mat_cap * 8;
+    // Second plan of CTA-per-env grids, used once the handle has received actions (buses may be split from then on):
+    // the F structure does not fit the small hybrid plan, explicit inverses with the whole SM's shared memory do better
+    // there (IEEE-118, random node-splitting agent: 0.56 M env-steps/s against 0.24 M).
+    env->alt_sparse = env->sparse; env->alt_mat_cap = env->mat_cap; env->alt_env_smem_bytes = env->env_smem_bytes;
+    if (tpe == 256 && env->sparse >= 2 && !getenv("PPN_NO_ALT_PLAN")) {
+        env->alt_sparse = 1; env->alt_mat_cap = plan(1); env->alt_env_smem_bytes = fixed + env->alt_mat_cap * 8;
     }
-    else if (cap > worst) cap = worst;                       // one env per CTA: take what the SM has
-    cap &= ~1;
-    env->mat_cap = cap;
-    env->env_smem_bytes = fixed + cap * 8;
     env->ws_stride = worst;
     env->ws_rows = n_envs;
     env->horizon = cfg->n_timesteps_horizon_maintenance > 0 ? cfg->n_timesteps_horizon_maintenance : 1;
@@ -261,6 +466,11 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     CK(cudaMalloc(&env->d_init, (size_t)2 * n_envs * sizeof(int32_t)));
     env->allocs.push_back(env->d_init);
     CK(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
+    if (env->alt_sparse != env->sparse) {
+        CK(cudaHostAlloc(&env->h_split, sizeof(int), cudaHostAllocMapped));
+        *env->h_split = 0;
+        CK(cudaHostGetDevicePointer(&env->d_split, env->h_split, 0));
+    }
     *out = env;
     return PPN_OK;
 }
@@ -274,6 +484,7 @@ extern "C" void ppn_destroy(ppn_env* env) {
     void* dev[] = {env->d_act, env->d_obs, env->d_reward, env->d_done, env->d_flag, env->d_ill};
     for (void* p : dev) if (p) cudaFree(p);
     if (env->own_stream) cudaStreamDestroy(env->own_stream);
+    if (env->h_split) cudaFreeHost(env->h_split);
     for (int i = 0; i < env->n_chunks; i++) if (env->chunk_stream[i]) cudaStreamDestroy(env->chunk_stream[i]);
     delete env;
 }
@@ -338,7 +549,11 @@ extern "C" int ppn_load_chronics(ppn_env* env, int n_chronics, const ppn_chronic
 }
 
 static int launch(ppn_env* env, PpnStepArgs& a, cudaStream_t s) {
-    a.ws = env->ws; a.ws_stride = env->ws_stride; a.mat_cap = env->mat_cap; a.stats = env->stats;
+    const bool alt = env->h_split && *(volatile int*)env->h_split != 0;   // may lag a launch or two: only a plan switch
+    a.split_flag = env->d_split;
+    const int smem_bytes = alt ? env->alt_env_smem_bytes : env->env_smem_bytes;
+    a.ws = env->ws; a.ws_stride = env->ws_stride; a.mat_cap = alt ? env->alt_mat_cap : env->mat_cap; a.stats = env->stats;
+    a.sparse = alt ? env->alt_sparse : env->sparse; a.ws_dense = env->ws_dense;
     if (a.n_envs <= 0) { a.n_envs = env->B; a.env_off = 0; }   // whole batch unless the caller set a chunk
     {   // observation rows as TMA bulk stores when every row starts on a 16-byte boundary
         static const int no_bulk = getenv("PPN_NO_BULK") != nullptr;
@@ -356,7 +571,7 @@ static int launch(ppn_env* env, PpnStepArgs& a, cudaStream_t s) {
             a.ws = nws;
         }
     }
-    int rc = ppn_launch_step(&env->dc, &env->dch, &env->dcfg, &env->st, &a, env->tpe, env->envs_per_block, env->env_smem_bytes, s);
+    int rc = ppn_launch_step(&env->dc, &env->dch, &env->dcfg, &env->st, &a, env->tpe, env->envs_per_block, smem_bytes, s);
     env->launches++;
     env->async_pending = true;
     if (rc != 0) return fail(env, PPN_E_CUDA, std::string("step kernel launch: ") + cudaGetErrorString((cudaError_t)rc));

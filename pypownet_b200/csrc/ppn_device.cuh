@@ -19,6 +19,49 @@
 #define PPN_BT_PV 2
 #define PPN_BT_REF 3
 
+// Static symbolic structure of the sparse LDL^T factorisation of B' / B'' / Bdc (all share the pattern of the line
+// graph; SHIFT = 0 makes them symmetric).  Rows follow a minimum-degree elimination order of the substation graph,
+// computed once per grid on the host.  Two structures per grid: U = one row per substation (no bus is split, the
+// common case), F = two adjacent rows per substation (bus s and its sister s+S).  Rows of buses that take no part in a
+// system (isolated, reference, PV for B'') are identity rows, so the pattern never changes with the topology.
+struct PpnDevSparse {
+    int n;                    // rows
+    int nnz;                  // off-diagonal entries of L
+    int n_lev;                // levels of the elimination tree
+    int cut_lev;              // hybrid solver: levels >= cut_lev (the narrow top of the elimination tree) form a dense block
+    int cut_row;              // first row of that block (rows are sorted by level)
+    int cut_ent;              // first entry whose column belongs to the block (entries are column-major)
+    int nt;                   // rows of the block
+    int blob_words;           // 32-bit words of the table blob
+    const int* blob;          // every table below in one contiguous block, so that a CTA can stage it in shared memory
+    // word offsets into the blob (int tables first, then the short tables)
+    int o_colptr;             // int   [n+1]  off-diagonal entries of L by column, rows ascending
+    int o_lev_ptr;            // int   [n_lev+1] into lev_ent
+    int o_lev_ent;            // int   targets of each level: entry id e < nnz, or nnz + column for a diagonal
+    int o_trip_ptr;           // int   [nnz+n+1] update terms of each target
+    int o_trip;               // int   (entry (i,k) << 16) | entry (j,k): target (i,j) -= T(i,k) L(j,k), k ascending
+    int o_line_pos;           // int   U: [N] entry of the line's off-diagonal term; F: [N][2][2] by (origin node, extremity node)
+    int o_rowptr;             // int   [n+1] entries of L by row (for the forward substitution), columns ascending
+    int o_rowent;             // int   [nnz] entry ids
+    int o_lev_rows_ptr;       // int   [n_lev+1] rows (= columns) of each level of the elimination tree
+    int o_lev_rows;           // int   [n]
+    int o_rpack;              // int   [nnz] row-wise entries packed as (8 * entry id << 16) | 8 * column (byte offsets)
+    int o_rowpk;              // int   [n] (first row-wise entry << 8) | number of entries of the row
+    int o_colpk;              // int   [n] (first column entry << 8) | number of entries of the column
+    int o_rowoff;             // short [nnz] 8 * row of each column-wise entry (byte offset into the solve vector)
+    int o_row_lev;            // short [n] level of each row
+    int o_rowidx;             // short [nnz]
+    int o_ecol;               // short [nnz] column of each entry
+    int o_parent;             // short [n] elimination tree (-1 root)
+    int o_bus_row;            // short [NB] row of bus b, -1 when the bus has no row (sisters in U)
+};
+
+// doubles of per-env storage of ONE factor: T[nnz], L[nnz], d[n] (doubles), entry / row offsets into the inverse
+// (int nnz + n), compact index of each row (short n)
+static inline __host__ __device__ int ppn_sp_factor_doubles(int n, int nnz) {
+    return 2 * nnz + n + (nnz + n + 1) / 2 + (n + 3) / 4;
+}
+
 struct PpnDevCase {
     int S, G, L, N, NB, A, OBSD;
     int slack_bus;
@@ -49,6 +92,7 @@ struct PpnDevCase {
     const double* load_qd0;
     const double* thermal;    // [N] amperes
     const uint8_t* line_status0;  // [N]
+    PpnDevSparse sp[2];       // [0] U (un-split grid), [1] F (any bus split)
 };
 
 // All chronics of a handle in ONE table of 32-bit words: each row is the record an env reads per timestep
@@ -109,8 +153,16 @@ struct PpnStepArgs {
     uint8_t* illegal;           // [rows][1+2N+S] or NULL
     double* ws;                 // global workspace for matrices that do not fit the shared-memory budget
     long long ws_stride;        // doubles per env
+    long long ws_dense;         // sparse solver: offset of the factor storage inside the env's slice
+    int sparse;                 // 0: dense Gauss-Jordan inverses; 1: sparse LDL^T on the static pattern, then explicit
+                                // inverses; 2: sparse LDL^T and level-scheduled triangular solves every half-iteration;
+                                // 3: hybrid -- sparse LDL^T for the wide bottom levels of the elimination tree, explicit
+                                // dense inverse of the Schur complement of its narrow top (a few dozen rows), so a solve
+                                // is a handful of wide parallel steps and no full dense matrix is ever stored
     int mat_cap;                // doubles of shared memory per env for B' and B''
     unsigned long long* stats;  // [8] or NULL
+    int* split_flag;            // page-locked host word (device alias) set to 1 when an env applies a node switch:
+                                // tells the host that buses may be split from now on (shared-memory plan), or NULL
 };
 
 // Shared-memory footprint of one env (bytes), excluding the matrix area.  Must match the carve-up in ppn_kernels.cu.

@@ -257,6 +257,539 @@ __device__ __noinline__ void gj16_rows_in_registers(unsigned m_s, int n, int ld,
     __syncwarp(syncmask);
 }
 
+// ------------------------------------------------------------------------------------- sparse LDL^T (static pattern)
+// Index tables of one structure (PpnDevSparse), read from the global blob or from its copy in shared memory.
+struct SpView {
+    int n, nnz, n_lev;
+    bool full;   // F structure: two rows per substation
+    const PpnDevSparse* d;   // the structure (table offsets)
+    unsigned tb;             // shared-window address of the staged tables when tables AND factors are in shared
+                             // memory (the LDS/STS code path of a CTA-per-env kernel), else 0
+    bool hyb;                // hybrid factor (dense inverse of the top block) -- needs tb
+    const int *colptr, *lev_ptr, *lev_ent, *trip_ptr, *trip, *line_pos, *rowptr, *rowent, *lev_rows_ptr, *lev_rows;
+    const short *rowidx, *ecol, *parent, *bus_row;
+};
+
+__device__ __forceinline__ SpView sp_view(const PpnDevSparse& sp, const int* base, int S) {
+    SpView v;
+    v.n = sp.n; v.nnz = sp.nnz; v.n_lev = sp.n_lev; v.full = sp.n > S; v.d = &sp; v.tb = 0; v.hyb = false;
+    v.colptr = base + sp.o_colptr; v.lev_ptr = base + sp.o_lev_ptr; v.lev_ent = base + sp.o_lev_ent;
+    v.trip_ptr = base + sp.o_trip_ptr; v.trip = base + sp.o_trip; v.line_pos = base + sp.o_line_pos;
+    v.rowptr = base + sp.o_rowptr; v.rowent = base + sp.o_rowent;
+    v.lev_rows_ptr = base + sp.o_lev_rows_ptr; v.lev_rows = base + sp.o_lev_rows;
+    v.rowidx = reinterpret_cast<const short*>(base + sp.o_rowidx); v.ecol = reinterpret_cast<const short*>(base + sp.o_ecol);
+    v.parent = reinterpret_cast<const short*>(base + sp.o_parent); v.bus_row = reinterpret_cast<const short*>(base + sp.o_bus_row);
+    return v;
+}
+
+// Storage of one factor (ppn_sp_factor_doubles): T[nnz] (entries times the pivot of their column), Lv[nnz] (unit lower
+// factor; holds the lower triangle of the matrix on entry), dg[n] (diagonal of the matrix on entry, pivots after the
+// factorisation, their reciprocals during the inversion), eoff[nnz] / koff[n] (offset into a column of the inverse of
+// each entry's row / of each row), cp[n] (compact index of each row's bus in the system being solved, or n_act for
+// rows that take no part = identity rows).
+struct SpFactor {
+    double* T; double* Lv; double* dg; int* eoff; int* koff; short* cp;
+};
+
+__device__ __forceinline__ SpFactor sp_carve(double* base, const SpView& sp, int which) {
+    SpFactor f;
+    double* p = base + which * ppn_sp_factor_doubles(sp.n, sp.nnz);
+    f.T = p; f.Lv = p + sp.nnz; f.dg = p + 2 * sp.nnz;
+    f.eoff = reinterpret_cast<int*>(p + 2 * sp.nnz + sp.n);
+    f.koff = f.eoff + sp.nnz;
+    f.cp = reinterpret_cast<short*>(p + 2 * sp.nnz + sp.n + (sp.nnz + sp.n + 1) / 2);
+    return f;
+}
+
+// identity start of a factor: no couplings, unit diagonal; cp = n_act for every row
+template <int TPE> __device__ __forceinline__ void sp_clear(const SpView& sp, const SpFactor& f, int n_act, int tid) {
+    for (int i = tid; i < sp.nnz; i += TPE) f.Lv[i] = 0.0;
+    for (int i = tid; i < sp.n; i += TPE) { f.dg[i] = 1.0; f.cp[i] = (short)n_act; }
+}
+
+// Left-looking numeric factorisation by levels of the elimination tree: every target (i,j) of a level gathers its
+// update terms in a fixed order (deterministic, no atomics), then the level's columns are scaled by their pivots.
+// NF = 2: B' and B'' side by side, one half of the env's threads each (same structure, shared barriers).
+template <int TPE, int NF> __device__ __forceinline__ void sp_factor(const SpView& sp, const SpFactor& f1, const SpFactor& f2, int tid,
+                                                                     unsigned mask) {
+    constexpr int H = TPE / NF;
+    const SpFactor& f = (NF == 1 || tid < H) ? f1 : f2;
+    const int ht = (NF == 1 || tid < H) ? tid : tid - H;
+    const int nnz = sp.nnz;
+    for (int lv = 0; lv < sp.n_lev; lv++) {
+        const int a = sp.lev_ptr[lv], b = sp.lev_ptr[lv + 1];
+        for (int q = a + ht; q < b; q += H) {
+            const int id = sp.lev_ent[q];
+            double acc = id < nnz ? f.Lv[id] : f.dg[id - nnz];
+            const int t1 = sp.trip_ptr[id + 1];
+            for (int t = sp.trip_ptr[id]; t < t1; t++) {
+                const unsigned pk = (unsigned)sp.trip[t];
+                acc = fma(-f.T[pk >> 16], f.Lv[pk & 0xffffu], acc);
+            }
+            if (id < nnz) f.T[id] = acc; else f.dg[id - nnz] = acc;
+        }
+        env_sync<TPE>(mask);
+        for (int q = a + ht; q < b; q += H) {
+            const int id = sp.lev_ent[q];
+            if (id < nnz) f.Lv[id] = f.T[id] / f.dg[sp.ecol[id]];
+        }
+        env_sync<TPE>(mask);
+    }
+}
+
+// pivots -> reciprocal pivots (once per factorisation, before the solves)
+template <int TPE> __device__ __forceinline__ void sp_recip(const SpView& sp, const SpFactor& f1, const SpFactor& f2, bool two, int tid,
+                                                            unsigned mask) {
+    for (int i = tid; i < sp.n; i += TPE) {
+        f1.dg[i] = 1.0 / f1.dg[i];
+        if (two) f2.dg[i] = 1.0 / f2.dg[i];
+    }
+    env_sync<TPE>(mask);
+}
+
+// L D L^T x = w in place (w: one value per row, zero on identity rows), level-scheduled: a row of the forward sweep
+// only gathers rows of lower levels of the elimination tree, a row of the backward sweep only rows of higher levels,
+// so the rows of one level run in parallel and every sum has a fixed order.
+template <int TPE> __device__ __forceinline__ void sp_solve(const SpView& sp, const SpFactor& f, double* w, int tid, unsigned mask) {
+    for (int lv = 1; lv < sp.n_lev; lv++) {   // rows of level 0 depend on nothing
+        const int q1 = sp.lev_rows_ptr[lv + 1];
+        for (int q = sp.lev_rows_ptr[lv] + tid; q < q1; q += TPE) {
+            const int i = sp.lev_rows[q];
+            double acc = w[i];
+            const int t1 = sp.rowptr[i + 1];
+            for (int t = sp.rowptr[i]; t < t1; t++) {
+                const int en = sp.rowent[t];
+                acc = fma(-f.Lv[en], w[sp.ecol[en]], acc);
+            }
+            w[i] = acc;
+        }
+        env_sync<TPE>(mask);
+    }
+    for (int lv = sp.n_lev - 1; lv >= 0; lv--) {
+        const int q1 = sp.lev_rows_ptr[lv + 1];
+        for (int q = sp.lev_rows_ptr[lv] + tid; q < q1; q += TPE) {
+            const int k = sp.lev_rows[q];
+            double acc = w[k] * f.dg[k];
+            const int e1 = sp.colptr[k + 1];
+            for (int en = sp.colptr[k]; en < e1; en++) acc = fma(-f.Lv[en], w[sp.rowidx[en]], acc);
+            w[k] = acc;
+        }
+        env_sync<TPE>(mask);
+    }
+}
+
+// ---- the same factorisation and solve for a CTA-per-env kernel whose tables and factors all sit in SHARED memory:
+// 32-bit shared-window addresses and LDS/STS only, every thread owns one row of the solve (its level and the bounds of
+// its row / column lists stay in registers), and only the warps that own rows meet at the per-level barrier.
+__device__ __forceinline__ int lds32(unsigned a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds16(unsigned a) {
+    short v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(a));
+    return (int)v;
+}
+
+struct SpsFactor { unsigned T, Lv, dg; };   // shared-window addresses of one factor's arrays
+
+template <int TPE> __device__ __forceinline__ void sps_factor2(const PpnDevSparse& sp, unsigned tb, const SpsFactor& f1, const SpsFactor& f2,
+                                                               int tid) {
+    constexpr int H = TPE / 2;
+    const SpsFactor f = tid < H ? f1 : f2;
+    const int ht = tid < H ? tid : tid - H;
+    const int nnz = sp.nnz;
+    const unsigned lev_ptr = tb + 4u * sp.o_lev_ptr, lev_ent = tb + 4u * sp.o_lev_ent, trip_ptr = tb + 4u * sp.o_trip_ptr,
+                   trip = tb + 4u * sp.o_trip, ecol = tb + 4u * sp.o_ecol;
+    int a = lds32(lev_ptr);
+    for (int lv = 0; lv < sp.n_lev; lv++) {
+        const int b = lds32(lev_ptr + 4u * (lv + 1));
+#pragma unroll 1
+        for (int q = a + ht; q < b; q += H) {
+            const int id = lds32(lev_ent + 4u * q);
+            const unsigned dst = id < nnz ? f.T + 8u * id : f.dg + 8u * (id - nnz);
+            double acc = lds64(id < nnz ? f.Lv + 8u * id : dst);
+            const int t1 = lds32(trip_ptr + 4u * (id + 1));
+#pragma unroll 1
+            for (int t = lds32(trip_ptr + 4u * id); t < t1; t++) {
+                const unsigned pk = (unsigned)lds32(trip + 4u * t);
+                acc = fma(-lds64(f.T + 8u * (pk >> 16)), lds64(f.Lv + 8u * (pk & 0xffffu)), acc);
+            }
+            sts64(dst, acc);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int q = a + ht; q < b; q += H) {
+            const int id = lds32(lev_ent + 4u * q);
+            if (id < nnz) sts64(f.Lv + 8u * id, lds64(f.T + 8u * id) / lds64(f.dg + 8u * lds16(ecol + 2u * id)));
+        }
+        __syncthreads();
+        a = b;
+    }
+}
+
+// ---- hybrid: sparse LDL^T below the cut, explicit dense inverse of the Schur complement of the top block ---------
+// The elimination tree of a power grid is wide at the bottom and ends in a long, narrow chain; level-scheduled
+// substitution crawls through that chain one dependent row at a time.  Cutting the tree where at most ~40 rows remain
+// leaves a few wide sparse levels plus one small dense block whose inverse Z is formed once per factorisation, so a
+// solve is (cut_lev - 1) sparse forward steps, one gather, one dense product and cut_lev sparse backward steps, each
+// spread over the CTA.  Z: nt x ldz per matrix.
+template <int TPE> __device__ __noinline__ void hyb_factor2(const PpnDevSparse& sp, unsigned tb, const SpsFactor& f1, const SpsFactor& f2,
+                                                               double* Z1, double* Z2, int ldz, int tid) {
+    constexpr int H = TPE / 2;
+    const bool second = tid >= H;
+    const SpsFactor f = second ? f2 : f1;
+    const int ht = second ? tid - H : tid;
+    const int nnz = sp.nnz, r0 = sp.cut_row, nt = sp.nt;
+    const unsigned lev_ptr = tb + 4u * sp.o_lev_ptr, lev_ent = tb + 4u * sp.o_lev_ent, trip_ptr = tb + 4u * sp.o_trip_ptr,
+                   trip = tb + 4u * sp.o_trip, ecol = tb + 4u * sp.o_ecol, rowidx = tb + 4u * sp.o_rowidx;
+    double* Z = second ? Z2 : Z1;
+    for (int i = ht; i < nt * ldz; i += H) Z[i] = 0.0;
+    __syncthreads();
+    int a = lds32(lev_ptr);
+    for (int lv = 0; lv < sp.cut_lev; lv++) {   // the sparse levels, as sps_factor2
+        const int b = lds32(lev_ptr + 4u * (lv + 1));
+#pragma unroll 1
+        for (int q = a + ht; q < b; q += H) {
+            const int id = lds32(lev_ent + 4u * q);
+            const unsigned dst = id < nnz ? f.T + 8u * id : f.dg + 8u * (id - nnz);
+            double acc = lds64(id < nnz ? f.Lv + 8u * id : dst);
+            const int t1 = lds32(trip_ptr + 4u * (id + 1));
+#pragma unroll 1
+            for (int t = lds32(trip_ptr + 4u * id); t < t1; t++) {
+                const unsigned pk = (unsigned)lds32(trip + 4u * t);
+                acc = fma(-lds64(f.T + 8u * (pk >> 16)), lds64(f.Lv + 8u * (pk & 0xffffu)), acc);
+            }
+            sts64(dst, acc);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int q = a + ht; q < b; q += H) {
+            const int id = lds32(lev_ent + 4u * q);
+            if (id < nnz) sts64(f.Lv + 8u * id, lds64(f.T + 8u * id) / lds64(f.dg + 8u * lds16(ecol + 2u * id)));
+        }
+        __syncthreads();
+        a = b;
+    }
+    // Schur complement of the top block: every structural entry of the block minus its update terms from the columns
+    // below the cut (the terms of a target are sorted by column, entries are numbered column-major)
+    const int q1 = lds32(lev_ptr + 4u * sp.n_lev);
+    const unsigned cut_ent = (unsigned)sp.cut_ent;
+#pragma unroll 1
+    for (int q = a + ht; q < q1; q += H) {
+        const int id = lds32(lev_ent + 4u * q);
+        int i, j;
+        double acc;
+        if (id < nnz) { i = lds16(rowidx + 2u * id); j = lds16(ecol + 2u * id); acc = lds64(f.Lv + 8u * id); }
+        else { i = j = id - nnz; acc = lds64(f.dg + 8u * i); }
+        const int t1 = lds32(trip_ptr + 4u * (id + 1));
+#pragma unroll 1
+        for (int t = lds32(trip_ptr + 4u * id); t < t1; t++) {
+            const unsigned pk = (unsigned)lds32(trip + 4u * t);
+            if ((pk & 0xffffu) >= cut_ent) break;
+            acc = fma(-lds64(f.T + 8u * (pk >> 16)), lds64(f.Lv + 8u * (pk & 0xffffu)), acc);
+        }
+        Z[(i - r0) * ldz + (j - r0)] = acc;
+        Z[(j - r0) * ldz + (i - r0)] = acc;
+    }
+    // reciprocal pivots of the sparse part
+    for (int k = ht; k < r0; k += H) sts64(f.dg + 8u * k, 1.0 / lds64(f.dg + 8u * k));
+    __syncthreads();
+}
+
+// Gauss-Jordan inverses of the two top blocks side by side, 64 threads each (warps 0-1: Z1, warps 2-3: Z2; the other
+// warps only meet the barriers).  The 64 threads form an 8 x 8 grid and thread (ti, tj) keeps the elements
+// (ti + 8a, tj + 8b), a, b < 5, in REGISTERS for the whole elimination (nt <= 40).  Per pivot the owners of column k
+// and of row k publish them, one barrier, every thread updates its registers from the two published vectors, one
+// barrier.  `buf`: 4 * nt doubles of scratch.  No pivoting (the Schur complement of a positive definite matrix is
+// positive definite); a singular block yields inf/NaN -> "diverging".
+template <int TPE> __device__ __noinline__ void hyb_invert2(double* Z1, double* Z2, int nt, int ldz, double* buf, int tid) {
+    constexpr int T = 5;
+    const bool work = tid < 128, second = tid >= 64;
+    const int ht = tid & 63, ti = ht >> 3, tj = ht & 7;
+    const unsigned z = saddr(second ? Z2 : Z1);
+    const unsigned col = saddr(buf) + (second ? 16u * (unsigned)nt : 0u), row = col + 8u * (unsigned)nt;
+    double v[T][T];
+    if (work) {
+#pragma unroll
+        for (int a = 0; a < T; a++)
+#pragma unroll
+            for (int b = 0; b < T; b++) {
+                const int i = ti + 8 * a, j = tj + 8 * b;
+                v[a][b] = (i < nt && j < nt) ? lds64(z + 8u * (unsigned)(i * ldz + j)) : 0.0;
+            }
+    }
+#pragma unroll 1
+    for (int k = 0; k < nt; k++) {
+        if (work) {
+            const int ka = k >> 3, kr = k & 7;
+            if (tj == kr) {   // my column kr + 8 ka is column k
+#pragma unroll
+                for (int a = 0; a < T; a++) {
+                    double x = v[a][0];
+#pragma unroll
+                    for (int b = 1; b < T; b++) x = ka == b ? v[a][b] : x;
+                    if (ti + 8 * a < nt) sts64(col + 8u * (unsigned)(ti + 8 * a), x);
+                }
+            }
+            if (ti == kr) {   // my row kr + 8 ka is row k
+#pragma unroll
+                for (int b = 0; b < T; b++) {
+                    double x = v[0][b];
+#pragma unroll
+                    for (int a = 1; a < T; a++) x = ka == a ? v[a][b] : x;
+                    if (tj + 8 * b < nt) sts64(row + 8u * (unsigned)(tj + 8 * b), x);
+                }
+            }
+        }
+        __syncthreads();
+        if (work) {
+            const double p = 1.0 / lds64(col + 8u * (unsigned)k);
+            double rw[T];
+#pragma unroll
+            for (int b = 0; b < T; b++) rw[b] = tj + 8 * b < nt ? lds64(row + 8u * (unsigned)(tj + 8 * b)) : 0.0;
+#pragma unroll
+            for (int a = 0; a < T; a++) {
+                const int i = ti + 8 * a;
+                if (i >= nt) continue;
+                if (i == k) {
+#pragma unroll
+                    for (int b = 0; b < T; b++) v[a][b] = (tj + 8 * b == k) ? p : v[a][b] * p;
+                } else {
+                    const double ci = lds64(col + 8u * (unsigned)i) * p;
+#pragma unroll
+                    for (int b = 0; b < T; b++) v[a][b] = (tj + 8 * b == k) ? -ci : fma(-ci, rw[b], v[a][b]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (work) {
+#pragma unroll
+        for (int a = 0; a < T; a++)
+#pragma unroll
+            for (int b = 0; b < T; b++) {
+                const int i = ti + 8 * a, j = tj + 8 * b;
+                if (i < nt && j < nt) sts64(z + 8u * (unsigned)(i * ldz + j), v[a][b]);
+            }
+    }
+    __syncthreads();
+}
+
+// (B)^-1 w in place with the hybrid factor.  dg: reciprocal pivots below the cut.  Four lanes share a row in every step
+// (the hub rows of a grid are long) and combine with two shuffles: fixed order, deterministic.
+template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp, unsigned tb, unsigned a_Lv, unsigned a_dg, const double* Z,
+                                                             int ldz, unsigned a_w, int tid) {
+    const unsigned a_lev = tb + 4u * sp.o_lev_rows_ptr, a_rowpk = tb + 4u * sp.o_rowpk, a_colpk = tb + 4u * sp.o_colpk,
+                   a_rpack = tb + 4u * sp.o_rpack, a_rowoff = tb + 4u * sp.o_rowoff, a_z = saddr(Z);
+    const int r0 = sp.cut_row, nt = sp.nt;
+    const int t = tid >> 2, part = tid & 3;
+    constexpr int RS = TPE / 4;   // rows per pass
+    int s0 = lds32(a_lev + 4u);
+    for (int lv = 1; lv < sp.cut_lev; lv++) {   // sparse forward steps (rows of level 0 depend on nothing)
+        const int s1 = lds32(a_lev + 4u * (lv + 1));
+#pragma unroll 1
+        for (int ib = s0; ib < s1; ib += RS) {
+            const int i = ib + t;
+            double y = 0.0;
+            if (i < s1) {
+                const unsigned pk = (unsigned)lds32(a_rowpk + 4u * i);
+                const int cnt = (int)(pk & 255u);
+                const unsigned ra = a_rpack + 4u * (pk >> 8);
+#pragma unroll 1
+                for (int q = part; q < cnt; q += 4) {
+                    const unsigned p0 = (unsigned)lds32(ra + 4u * q);
+                    y = fma(-lds64(a_Lv + (p0 >> 16)), lds64(a_w + (p0 & 0xffffu)), y);
+                }
+            }
+            y += __shfl_xor_sync(PPN_FULL, y, 1);
+            y += __shfl_xor_sync(PPN_FULL, y, 2);
+            if (i < s1 && part == 0) sts64(a_w + 8u * i, lds64(a_w + 8u * i) + y);
+        }
+        __syncthreads();
+        s0 = s1;
+    }
+    // top block: y2 = w2 - L21 y1 (entries below the cut only)
+    {
+        double y = 0.0;
+        if (t < nt) {
+            const unsigned pk = (unsigned)lds32(a_rowpk + 4u * (r0 + t));
+            const int cnt = (int)(pk & 255u);
+            const unsigned ra = a_rpack + 4u * (pk >> 8), cutoff = 8u * (unsigned)r0;
+#pragma unroll 1
+            for (int q = part; q < cnt; q += 4) {
+                const unsigned p0 = (unsigned)lds32(ra + 4u * q);
+                if ((p0 & 0xffffu) < cutoff) y = fma(-lds64(a_Lv + (p0 >> 16)), lds64(a_w + (p0 & 0xffffu)), y);
+            }
+        }
+        y += __shfl_xor_sync(PPN_FULL, y, 1);
+        y += __shfl_xor_sync(PPN_FULL, y, 2);
+        if (t < nt && part == 0) sts64(a_w + 8u * (r0 + t), lds64(a_w + 8u * (r0 + t)) + y);
+    }
+    __syncthreads();
+    // x2 = Z y2
+    {
+        double x = 0.0, x2 = 0.0;
+        if (t < nt) {
+            const unsigned zr = a_z + 8u * (unsigned)(t * ldz), wr = a_w + 8u * r0;
+            int j = part;
+#pragma unroll 1
+            for (; j + 4 < nt; j += 8) {
+                const double z0 = lds64(zr + 8u * j), z1 = lds64(zr + 8u * j + 32u);
+                const double w0 = lds64(wr + 8u * j), w1 = lds64(wr + 8u * j + 32u);
+                x = fma(z0, w0, x);
+                x2 = fma(z1, w1, x2);
+            }
+            if (j < nt) x = fma(lds64(zr + 8u * j), lds64(wr + 8u * j), x);
+            x += x2;
+        }
+        x += __shfl_xor_sync(PPN_FULL, x, 1);
+        x += __shfl_xor_sync(PPN_FULL, x, 2);
+        __syncthreads();
+        if (t < nt && part == 0) sts64(a_w + 8u * (r0 + t), x);
+    }
+    __syncthreads();
+    int e1 = r0;
+    for (int lv = sp.cut_lev - 1; lv >= 0; lv--) {   // sparse backward steps
+        const int e0 = lds32(a_lev + 4u * lv);
+#pragma unroll 1
+        for (int ib = e0; ib < e1; ib += RS) {
+            const int i = ib + t;
+            double y = 0.0;
+            if (i < e1) {
+                const unsigned pk = (unsigned)lds32(a_colpk + 4u * i);
+                const int cnt = (int)(pk & 255u);
+                const unsigned en0 = pk >> 8;
+#pragma unroll 1
+                for (int q = part; q < cnt; q += 4)
+                    y = fma(-lds64(a_Lv + 8u * (en0 + q)), lds64(a_w + lds16(a_rowoff + 2u * (en0 + q))), y);
+            }
+            y += __shfl_xor_sync(PPN_FULL, y, 1);
+            y += __shfl_xor_sync(PPN_FULL, y, 2);
+            if (i < e1 && part == 0) sts64(a_w + 8u * i, fma(lds64(a_w + 8u * i), lds64(a_dg + 8u * i), y));
+        }
+        __syncthreads();
+        e1 = e0;
+    }
+}
+
+// L D L^T x = w in place; dg holds the RECIPROCAL pivots.  The rows of a level are contiguous (the host sorts the
+// elimination order by level), so ONE warp walks the levels with nothing but __syncwarp between them -- no CTA
+// barrier per level -- while the other warps of the CTA wait at the closing barrier without using issue slots.
+// Every address is a 32-bit shared-window address hoisted out of the loops; the tables hold byte offsets.
+__device__ __forceinline__ void sps_solve_warp(unsigned a_lev, unsigned a_rowpk, unsigned a_colpk, unsigned a_rpack, unsigned a_rowoff,
+                                               unsigned a_Lv, unsigned a_dg, unsigned a_w, int n_lev, int lane) {
+    int s0 = lds32(a_lev + 4u);
+    for (int lv = 1; lv < n_lev; lv++) {   // forward: rows of level 0 depend on nothing
+        const int s1 = lds32(a_lev + 4u * (lv + 1));
+#pragma unroll 1
+        for (int i = s0 + lane; i < s1; i += 32) {
+            const unsigned pk = (unsigned)lds32(a_rowpk + 4u * i);
+            const unsigned wi = a_w + 8u * i;
+            double acc = lds64(wi);
+            unsigned ra = a_rpack + 4u * (pk >> 8);
+            int cnt = (int)(pk & 255u);
+#pragma unroll 1
+            for (; cnt >= 2; cnt -= 2, ra += 8u) {   // two entries per trip, loads first
+                const unsigned p0 = (unsigned)lds32(ra), p1 = (unsigned)lds32(ra + 4u);
+                const double l0 = lds64(a_Lv + (p0 >> 16)), x0 = lds64(a_w + (p0 & 0xffffu));
+                const double l1 = lds64(a_Lv + (p1 >> 16)), x1 = lds64(a_w + (p1 & 0xffffu));
+                acc = fma(-l0, x0, acc);
+                acc = fma(-l1, x1, acc);
+            }
+            if (cnt) {
+                const unsigned p0 = (unsigned)lds32(ra);
+                acc = fma(-lds64(a_Lv + (p0 >> 16)), lds64(a_w + (p0 & 0xffffu)), acc);
+            }
+            sts64(wi, acc);
+        }
+        __syncwarp();
+        s0 = s1;
+    }
+    int e1 = lds32(a_lev + 4u * n_lev);
+    for (int lv = n_lev - 1; lv >= 0; lv--) {   // diagonal and backward
+        const int e0 = lds32(a_lev + 4u * lv);
+#pragma unroll 1
+        for (int i = e0 + lane; i < e1; i += 32) {
+            const unsigned pk = (unsigned)lds32(a_colpk + 4u * i);
+            const unsigned wi = a_w + 8u * i;
+            double acc = lds64(wi) * lds64(a_dg + 8u * i);
+            unsigned en = pk >> 8;
+            int cnt = (int)(pk & 255u);
+#pragma unroll 1
+            for (; cnt >= 2; cnt -= 2, en += 2u) {
+                const int r0 = lds16(a_rowoff + 2u * en), r1 = lds16(a_rowoff + 2u * en + 2u);
+                const double l0 = lds64(a_Lv + 8u * en), l1 = lds64(a_Lv + 8u * en + 8u);
+                const double x0 = lds64(a_w + r0), x1 = lds64(a_w + r1);
+                acc = fma(-l0, x0, acc);
+                acc = fma(-l1, x1, acc);
+            }
+            if (cnt) acc = fma(-lds64(a_Lv + 8u * en), lds64(a_w + lds16(a_rowoff + 2u * en)), acc);
+            sts64(wi, acc);
+        }
+        __syncwarp();
+        e1 = e0;
+    }
+}
+
+template <int TPE> __device__ __forceinline__ void sps_solve(const PpnDevSparse& sp, unsigned tb, unsigned a_Lv, unsigned a_dg, unsigned w,
+                                                             int tid) {
+    if (tid < 32)
+        sps_solve_warp(tb + 4u * sp.o_lev_rows_ptr, tb + 4u * sp.o_rowpk, tb + 4u * sp.o_colpk, tb + 4u * sp.o_rpack,
+                       tb + 4u * sp.o_rowoff, a_Lv, a_dg, w, sp.n_lev, tid);
+    __syncthreads();
+}
+
+// Explicit inverses of the active parts of the factored matrices, one column per thread (the columns of both
+// matrices are spread over the env's threads in one go): forward substitution of a unit vector only walks the
+// elimination-tree path of its row, the backward sweep is the same instruction stream for every thread (uniform
+// index loads).  M: (n_act + 1) x ld, row n_act is the landing row of the identity rows.
+template <int TPE> __device__ __forceinline__ void sp_invert(const SpView& sp, const SpFactor& f1, const SpFactor& f2,
+                                                             const short* colbus1, const short* colbus2, double* M1, double* M2,
+                                                             int n1, int n2, int ld1, int ld2, int tid, unsigned mask) {
+    // reciprocal pivots and the offsets of every row / entry inside a column of the inverse
+    for (int i = tid; i < sp.n; i += TPE) {
+        f1.dg[i] = 1.0 / f1.dg[i]; f1.koff[i] = f1.cp[i] * ld1;
+        if (n2 > 0) { f2.dg[i] = 1.0 / f2.dg[i]; f2.koff[i] = f2.cp[i] * ld2; }
+    }
+    for (int i = tid; i < sp.nnz; i += TPE) {
+        const int r = sp.rowidx[i];
+        f1.eoff[i] = f1.cp[r] * ld1;
+        if (n2 > 0) f2.eoff[i] = f2.cp[r] * ld2;
+    }
+    env_sync<TPE>(mask);
+    for (int cc = tid; cc < n1 + n2; cc += TPE) {
+        const bool second = cc >= n1;
+        const SpFactor& f = second ? f2 : f1;
+        const int c = second ? cc - n1 : cc, n_act = second ? n2 : n1, ld = second ? ld2 : ld1;
+        double* x = (second ? M2 : M1) + c;
+        for (int r = 0; r <= n_act; r++) x[r * ld] = 0.0;
+        const int jr = sp.bus_row[(second ? colbus2 : colbus1)[c]];
+        x[f.koff[jr]] = 1.0;
+        for (int k = jr; k >= 0; k = sp.parent[k]) {
+            double* xk = x + f.koff[k];
+            const double yk = *xk;
+            const int e1 = sp.colptr[k + 1];
+            for (int e = sp.colptr[k]; e < e1; e++) {
+                double* t = x + f.eoff[e];
+                *t = fma(-f.Lv[e], yk, *t);
+            }
+            *xk = yk * f.dg[k];
+        }
+        int e = sp.nnz;
+        for (int k = sp.n - 1; k >= 0; k--) {
+            double* t = x + f.koff[k];
+            double sacc = *t;
+            const int e0 = sp.colptr[k];
+            for (int q = e0; q < e; q++) sacc = fma(-f.Lv[q], x[f.eoff[q]], sacc);
+            e = e0;
+            *t = sacc;
+        }
+    }
+    env_sync<TPE>(mask);
+}
+
 // dot product of a matrix row with a vector, four independent accumulation chains
 __device__ __forceinline__ double row_dot(const double* m, const double* x, int n) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -484,34 +1017,65 @@ __device__ __forceinline__ bool mismatch(Env<TPE, D>& e, const PpnDevCase& c, do
 
 // rundcpf on the prepared env: B theta = Pbus on pv+pq, Vm := 1.  M1 = n1 x n1 work matrix.
 template <int TPE, int MAXR, class D>
-__device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, double* M1, int n1, int ld1, int ref) {
+__device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, double* M1, int n1, int ld1, int ref,
+                                         const SpView* sp, double* spb, bool solve_mode) {
     const int NB = e.NB, S = e.S, tid = e.tid;
     const unsigned mask = e.mask;
     bool success;
     // ================= rundcpf: B theta = Pbus on pv+pq, Vm := 1
-    for (int i = tid; i < n1 * ld1; i += TPE) M1[i] = 0.0;
+    SpFactor f1{};
+    if (sp) { f1 = sp_carve(spb, *sp, 0); sp_clear<TPE>(*sp, f1, n1, tid); }
+    else for (int i = tid; i < n1 * ld1; i += TPE) M1[i] = 0.0;
+    if (solve_mode) for (int i = tid; i < NB; i += TPE) e.ydr()[i] = 0.0;   // right-hand side by row (ydr is free in DC mode)
     env_sync<TPE>(mask);
     const double va_ref = e.va()[ref] * (PPN_PI / 180.0);
     for (int i = tid; i < n1; i += TPE) {
         const int b = e.busp()[i];
         PPN_ENTRIES(e, c, b, k0, step)
         const int nent = e.deg()[b];
+        const int row = sp ? sp->bus_row[b] : 0;
         double diag = 0.0, bref = 0.0;
         for (int q = 0; q < nent; q++) {
             const int k = k0 + step * q;
             const int o = e.eoth()[k];
-            const double w = c.line_bdc[e.eline()[k] >> 1];
+            const int l = e.eline()[k] >> 1;
+            const double w = c.line_bdc[l];
             diag += w;
-            if (o != ref) M1[i * ld1 + e.idxp()[o]] -= w; else bref -= w;
+            if (o == ref) bref -= w;
+            else if (!sp) M1[i * ld1 + e.idxp()[o]] -= w;
+            else if (row > sp->bus_row[o]) f1.Lv[sp->line_pos[sp->full ? 4 * l + 2 * e.onode()[l] + e.enode()[l] : l]] -= w;
         }
-        M1[i * ld1 + i] += diag;
+        if (sp) { f1.dg[row] = diag; f1.cp[row] = (short)i; }
+        else M1[i * ld1 + i] += diag;
         // rhs = Pbus[pvpq] - B[pvpq, ref] Va0[ref], Pbus = Re(Sbus) - Gs/baseMVA
-        e.P()[i] = (e.pin()[b] - c.bus_ysh_r[b]) - bref * va_ref;
+        const double rhs = (e.pin()[b] - c.bus_ysh_r[b]) - bref * va_ref;
+        if (solve_mode) e.ydr()[row] = rhs; else e.P()[i] = rhs;
     }
     env_sync<TPE>(mask);
-    gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
-    for (int i = tid; i < n1; i += TPE) {
-        e.Q()[i] = row_dot(M1 + i * ld1, e.P(), n1);  // theta (radians) of pvpq bus i
+    if (solve_mode && TPE > 32 && sp->hyb) {
+        const int ldz = sp->d->nt | 1;
+        double* Z1 = spb + 2 * ppn_sp_factor_doubles(sp->n, sp->nnz);
+        const SpsFactor s1{saddr(f1.T), saddr(f1.Lv), saddr(f1.dg)};
+        // both halves of the CTA factor the same matrix into the same places (identical values): keeps one code path
+        hyb_factor2<TPE>(*sp->d, sp->tb, s1, s1, Z1, Z1, ldz, tid);
+        hyb_invert2<TPE>(Z1, Z1 + sp->d->nt * ldz, sp->d->nt, ldz, e.vr(), tid);   // vr | vi: 2 NB doubles of scratch in DC mode
+        hyb_solve<TPE>(*sp->d, sp->tb, s1.Lv, s1.dg, Z1, ldz, saddr(e.ydr()), tid);
+        for (int i = tid; i < n1; i += TPE) e.Q()[i] = e.ydr()[sp->bus_row[e.busp()[i]]];
+    } else if (solve_mode) {
+        sp_factor<TPE, 1>(*sp, f1, f1, tid, mask);
+        sp_recip<TPE>(*sp, f1, f1, false, tid, mask);
+        if (TPE > 32 && sp->tb) sps_solve<TPE>(*sp->d, sp->tb, saddr(f1.Lv), saddr(f1.dg), saddr(e.ydr()), tid);
+        else sp_solve<TPE>(*sp, f1, e.ydr(), tid, mask);
+        for (int i = tid; i < n1; i += TPE) e.Q()[i] = e.ydr()[sp->bus_row[e.busp()[i]]];
+    } else {
+        if (sp) {
+            sp_factor<TPE, 1>(*sp, f1, f1, tid, mask);
+            sp_invert<TPE>(*sp, f1, f1, e.busp(), e.busp(), M1, M1, n1, 0, ld1, ld1, tid, mask);
+        }
+        else gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
+        for (int i = tid; i < n1; i += TPE) {
+            e.Q()[i] = row_dot(M1 + i * ld1, e.P(), n1);  // theta (radians) of pvpq bus i
+        }
     }
     env_sync<TPE>(mask);
     for (int b = tid; b < NB; b += TPE) {
@@ -553,7 +1117,8 @@ __device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, do
 // compile to LDS/STS) or in the env's slice of the HBM workspace.
 template <int TPE, int MAXR, class D, bool SMEM>
 __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevCfg& cfg, double* M1, double* M2,
-                                         int n1, int n2, int ld1, int ld2, int ref, int slot, int& n_iter) {
+                                         int n1, int n2, int ld1, int ld2, int ref, int slot, int& n_iter,
+                                         const SpView* sp, double* spb, bool solve_mode) {
     const int NB = e.NB, S = e.S, tid = e.tid;
     const unsigned mask = e.mask;
     bool success;
@@ -565,6 +1130,10 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
     constexpr int RB = TPE > 32 ? 1 : (D::NB_MAX > 0 ? (D::NB_MAX + TPE - 1) / TPE : 2);
     double r_vm[RB], r_rvm[RB], r_va[RB], r_cs[RB], r_sn[RB], r_pin[RB], r_qin[RB], r_ydr[RB], r_ydi[RB], r_sr[RB], r_si[RB];
     int r_t[RB], r_ip[RB], r_iq[RB], r_deg[RB], r_k0[RB], r_step[RB];
+    // solve mode: the mismatch vectors are indexed by factor row (zero on the identity rows) and are solved in place
+    if (solve_mode) {
+        for (int i = tid; i < 2 * NB; i += TPE) e.P()[i] = 0.0;   // P | Q are adjacent
+    }
     PPN_TICK(4);
     // V0 from the stored state; on-line generators impose their set-point magnitude
 #pragma unroll
@@ -592,15 +1161,23 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         r_va[r] = atan2(vi, vr);           // radians
         r_cs[r] = vr / vm; r_sn[r] = vi / vm;
         r_pin[r] = e.pin()[b]; r_qin[r] = e.qin()[b];
-        r_ip[r] = t != PPN_BT_REF ? e.idxp()[b] : 0;
-        r_iq[r] = t == PPN_BT_PQ ? e.idxq()[b] : 0;
+        r_ip[r] = t != PPN_BT_REF ? (solve_mode ? (int)sp->bus_row[b] : (int)e.idxp()[b]) : 0;
+        r_iq[r] = t == PPN_BT_PQ ? (solve_mode ? (int)sp->bus_row[b] : (int)e.idxq()[b]) : 0;
         r_deg[r] = e.deg()[b];
         r_step[r] = b >= S ? -1 : 1;
         r_k0[r] = b >= S ? c.adj_ptr[s + 1] - 1 : c.adj_ptr[s];
     }
     PPN_TICK(5);
     // B' (r = 0, no charging, no shunts, unit taps) over pv+pq; B'' = -Im(Ybus) over pq; Ybus diagonal
-    for (int i = tid; i < n1 * ld1 + n2 * ld2; i += TPE) M1[i] = 0.0;
+    // dense: assembled in place in M1 / M2; sparse: lower triangle into the static pattern, each entry written by the
+    // thread that owns the bus with the larger row (parallel lines accumulate in that bus's list order)
+    SpFactor f1{}, f2{};
+    if (sp) {
+        f1 = sp_carve(spb, *sp, 0); f2 = sp_carve(spb, *sp, 1);
+        sp_clear<TPE>(*sp, f1, n1, tid); sp_clear<TPE>(*sp, f2, n2, tid);
+    } else {
+        for (int i = tid; i < n1 * ld1 + n2 * ld2; i += TPE) M1[i] = 0.0;
+    }
     env_sync<TPE>(mask);
 #pragma unroll
     for (int r = 0; r < RB; r++) {
@@ -609,6 +1186,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         const int b = tid + r * TPE;
         const bool ispq = t == PPN_BT_PQ, inp = t != PPN_BT_REF;
         const int i = r_ip[r], iq = r_iq[r];
+        const int row = sp ? sp->bus_row[b] : 0;
         double d1 = 0.0, yr = c.bus_ysh_r[b], yi = c.bus_ysh_i[b];
         for (int q = 0; q < r_deg[r]; q++) {
             const int k = r_k0[r] + r_step[r] * q;
@@ -620,12 +1198,23 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
             yi += y[1];
             d1 += w;
             const int to = e.btype()[o];
-            if (inp && to != PPN_BT_REF) M1[i * ld1 + e.idxp()[o]] -= w;
-            if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= e.eyi()[k];
+            if (!sp) {
+                if (inp && to != PPN_BT_REF) M1[i * ld1 + e.idxp()[o]] -= w;
+                if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= e.eyi()[k];
+            } else if (row > sp->bus_row[o]) {
+                const int pos = sp->line_pos[sp->full ? 4 * l + 2 * e.onode()[l] + e.enode()[l] : l];
+                if (inp && to != PPN_BT_REF) f1.Lv[pos] -= w;
+                if (ispq && to == PPN_BT_PQ) f2.Lv[pos] -= e.eyi()[k];
+            }
         }
         r_ydr[r] = yr; r_ydi[r] = yi;
-        if (inp) M1[i * ld1 + i] += d1;
-        if (ispq) M2[iq * ld2 + iq] += -yi;
+        if (!sp) {
+            if (inp) M1[i * ld1 + i] += d1;
+            if (ispq) M2[iq * ld2 + iq] += -yi;
+        } else {
+            if (inp) { f1.dg[row] = d1; f1.cp[row] = (short)e.idxp()[b]; }
+            if (ispq) { f2.dg[row] = -yi; f2.cp[row] = (short)e.idxq()[b]; }
+        }
     }
     env_sync<TPE>(mask);
     // fdpf: evaluate, then alternate P (angle) and Q (magnitude) half-iterations, testing after each
@@ -637,18 +1226,33 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         long long t_a = clock64();
 #endif
         if (half > 0) {
+            if (solve_mode) {   // B'^-1 P or B''^-1 Q in place (every thread takes part)
+#ifdef PPN_TIMING
+                long long t_s = clock64();
+#endif
+                const SpFactor& fh = (half & 1) ? f1 : f2;
+                double* wh = (half & 1) ? e.P() : e.Q();
+                if (TPE > 32 && sp->hyb) {
+                    const int ldz = sp->d->nt | 1;
+                    const double* Zh = spb + 2 * ppn_sp_factor_doubles(sp->n, sp->nnz) + ((half & 1) ? 0 : sp->d->nt * ldz);
+                    hyb_solve<TPE>(*sp->d, sp->tb, saddr(fh.Lv), saddr(fh.dg), Zh, ldz, saddr(wh), tid);
+                }
+                else if (TPE > 32 && sp->tb) sps_solve<TPE>(*sp->d, sp->tb, saddr(fh.Lv), saddr(fh.dg), saddr(wh), tid);
+                else sp_solve<TPE>(*sp, fh, wh, tid, mask);
+                PPN_TICK_ACC(23, t_s);   // triangular solves
+            }
 #pragma unroll
             for (int r = 0; r < RB; r++) {
                 const int t = r_t[r];
                 const int b = tid + r * TPE;
                 if (half & 1) {   // P iteration: Va[pvpq] -= B'^-1 P
                     if (t == PPN_BT_PV || t == PPN_BT_PQ) {
-                        r_va[r] -= row_dot(M1 + r_ip[r] * ld1, e.P(), n1);
+                        r_va[r] -= solve_mode ? e.P()[r_ip[r]] : row_dot(M1 + r_ip[r] * ld1, e.P(), n1);
                         sincos(r_va[r], &r_sn[r], &r_cs[r]);
                         e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
                     }
                 } else if (t == PPN_BT_PQ) {   // Q iteration: Vm[pq] -= B''^-1 Q
-                    r_vm[r] -= row_dot(M2 + r_iq[r] * ld2, e.Q(), n2);
+                    r_vm[r] -= solve_mode ? e.Q()[r_iq[r]] : row_dot(M2 + r_iq[r] * ld2, e.Q(), n2);
                     r_rvm[r] = 1.0 / r_vm[r];
                     e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
                 }
@@ -697,7 +1301,22 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         if (half == 2 * cfg.max_it) break;
         if (half == 0) {
             PPN_TICK(7);
-            if (TPE == 32 && SMEM && n1 <= 16 && n2 <= 16) {
+            if (sp && TPE > 32 && sp->hyb) {
+                const int ldz = sp->d->nt | 1;
+                double* Z1 = spb + 2 * ppn_sp_factor_doubles(sp->n, sp->nnz);
+                hyb_factor2<TPE>(*sp->d, sp->tb, SpsFactor{saddr(f1.T), saddr(f1.Lv), saddr(f1.dg)},
+                                 SpsFactor{saddr(f2.T), saddr(f2.Lv), saddr(f2.dg)}, Z1, Z1 + sp->d->nt * ldz, ldz, tid);
+                PPN_TICK(8);
+                hyb_invert2<TPE>(Z1, Z1 + sp->d->nt * ldz, sp->d->nt, ldz, e.ydr(), tid);   // ydr | ydi: 2 NB doubles, the Ybus diagonal lives in registers here
+            } else if (sp) {
+                if (TPE > 32 && sp->tb)
+                    sps_factor2<TPE>(*sp->d, sp->tb, SpsFactor{saddr(f1.T), saddr(f1.Lv), saddr(f1.dg)},
+                                     SpsFactor{saddr(f2.T), saddr(f2.Lv), saddr(f2.dg)}, tid);
+                else sp_factor<TPE, 2>(*sp, f1, f2, tid, mask);
+                PPN_TICK(8);
+                if (solve_mode) sp_recip<TPE>(*sp, f1, f2, true, tid, mask);
+                else sp_invert<TPE>(*sp, f1, f2, e.busp(), e.busq(), M1, M2, n1, n2, ld1, ld2, tid, mask);
+            } else if (TPE == 32 && SMEM && n1 <= 16 && n2 <= 16) {
                 // both inverses at once: lanes 0-15 hold the rows of B', lanes 16-31 those of B''
                 const int hf = tid >> 4;
                 gj16_rows_in_registers(saddr(hf ? M2 : M1), hf ? n2 : n1, hf ? ld2 : ld1, tid & 15,
@@ -706,7 +1325,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                 gj_invert<TPE, MAXR>(M1, n1, ld1, tid, mask);
                 gj_invert<TPE, MAXR>(M2, n2, ld2, tid, mask);
             }
-            PPN_TICK(8);
+            if (!sp) PPN_TICK(8);
             PPN_TICK(9);
         }
         half++;
@@ -885,14 +1504,59 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
     // ---- matrices: shared memory when they fit, else the env's slice of the global workspace
     const int ld1 = n1 | 1, ld2 = n2 | 1;
     bool success;
-    if (n1 * ld1 + n2 * ld2 <= args.mat_cap) {
+    if (args.sparse) {
+        // sparse LDL^T on the static pattern (U while no sister bus is in use, else F), then explicit inverses with
+        // one landing row each; the factor storage sits behind the inverses when shared memory has room for it
+        bool split = false;
+        for (int b = S + tid; b < NB; b += TPE) split |= e.btype()[b] != PPN_BT_ISOLATED;
+        const int which = env_any<TPE>(split, mask) ? 1 : 0;
+        const PpnDevSparse& spd = c.sp[which];
+        const bool solve_mode = args.sparse >= 2;
+        const int dense_need = solve_mode ? 0 : (n1 + 1) * ld1 + (cfg.dc ? 0 : (n2 + 1) * ld2);
+        const int val_need = 2 * ppn_sp_factor_doubles(spd.n, spd.nnz) + (args.sparse == 3 ? 2 * spd.nt * (spd.nt | 1) : 0),
+                  blob_dbl = spd.blob_words / 2;
+        double* wsrow = args.ws + (size_t)slot * args.ws_stride;
+        // index tables: staged once per CTA at the end of the matrix area when everything fits (they stay there
+        // across the load-flows of this step), else read from global memory
+        const int* tables = spd.blob;
+        if (dense_need + val_need + blob_dbl <= args.mat_cap) {
+            int* dst = reinterpret_cast<int*>(e.mat() + (args.mat_cap - blob_dbl));
+            if (e.misc()[3] != which) {
+                env_sync<TPE>(mask);
+                for (int i = tid; i < spd.blob_words; i += TPE) dst[i] = spd.blob[i];
+                if (tid == 0) e.misc()[3] = which;
+                env_sync<TPE>(mask);
+            }
+            tables = dst;
+        } else {
+            env_sync<TPE>(mask);
+            if (tid == 0) e.misc()[3] = -1;   // the dense part may overwrite a staged copy
+        }
+        SpView spv = sp_view(spd, tables, S);
+        if (TPE > 32 && tables != spd.blob && dense_need + val_need <= args.mat_cap) {
+            spv.tb = saddr(tables);
+            spv.hyb = args.sparse == 3;
+        }
+        const SpView* sp = &spv;
+        if (dense_need <= args.mat_cap) {
+            double* M1 = e.mat();
+            double* spb = dense_need + val_need <= args.mat_cap ? M1 + dense_need : wsrow + args.ws_dense;
+            success = cfg.dc ? dc_solve<TPE, MAXR, D>(e, c, M1, n1, ld1, ref, sp, spb, solve_mode)
+                             : ac_solve<TPE, MAXR, D, true>(e, c, cfg, M1, M1 + (n1 + 1) * ld1, n1, n2, ld1, ld2, ref, slot, n_iter, sp, spb, solve_mode);
+        } else {
+            double* M1 = wsrow;
+            double* spb = wsrow + args.ws_dense;
+            success = cfg.dc ? dc_solve<TPE, MAXR, D>(e, c, M1, n1, ld1, ref, sp, spb, false)
+                             : ac_solve<TPE, MAXR, D, false>(e, c, cfg, M1, M1 + (n1 + 1) * ld1, n1, n2, ld1, ld2, ref, slot, n_iter, sp, spb, false);
+        }
+    } else if (n1 * ld1 + n2 * ld2 <= args.mat_cap) {
         double* M1 = e.mat();
-        success = cfg.dc ? dc_solve<TPE, MAXR, D>(e, c, M1, n1, ld1, ref)
-                         : ac_solve<TPE, MAXR, D, true>(e, c, cfg, M1, M1 + n1 * ld1, n1, n2, ld1, ld2, ref, slot, n_iter);
+        success = cfg.dc ? dc_solve<TPE, MAXR, D>(e, c, M1, n1, ld1, ref, nullptr, nullptr, false)
+                         : ac_solve<TPE, MAXR, D, true>(e, c, cfg, M1, M1 + n1 * ld1, n1, n2, ld1, ld2, ref, slot, n_iter, nullptr, nullptr, false);
     } else {
         double* M1 = args.ws + (size_t)slot * args.ws_stride;
-        success = cfg.dc ? dc_solve<TPE, MAXR, D>(e, c, M1, n1, ld1, ref)
-                         : ac_solve<TPE, MAXR, D, false>(e, c, cfg, M1, M1 + n1 * ld1, n1, n2, ld1, ld2, ref, slot, n_iter);
+        success = cfg.dc ? dc_solve<TPE, MAXR, D>(e, c, M1, n1, ld1, ref, nullptr, nullptr, false)
+                         : ac_solve<TPE, MAXR, D, false>(e, c, cfg, M1, M1 + n1 * ld1, n1, n2, ld1, ld2, ref, slot, n_iter, nullptr, nullptr, false);
     }
     PPN_TICK(11);
     // runpf tail: out-of-service generators report Pg = Qg = 0
@@ -1096,6 +1760,7 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
     const bool is_sim = mode == PPN_MODE_SIMULATE;
     if (mode == PPN_MODE_GAME_OVER && args.mask && !args.mask[env]) return;
 
+    if (tid == 0) e.misc()[3] = -1;   // no sparse index tables staged yet
     // ---- state in
     if (mode == PPN_MODE_INIT) {
         for (int b = tid; b < NB; b += TPE) { e.vm()[b] = c.bus_vm0[b]; e.va()[b] = c.bus_va0[b]; }
@@ -1196,6 +1861,7 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
             for (int s = tid; s < S; s += TPE)
                 if (e.subch()[s]) e.nreact()[s] = cfg.n_node_react;
             cost_nodes = env_sum_int<TPE>(cn, e.redi(), tid, mask);
+            if (cost_nodes > 0 && tid == 0 && args.split_flag && !is_sim) *args.split_flag = 1;
             cost_lines = env_sum_int<TPE>(cl, e.redi() + (TPE + 31) / 32, tid, mask);
             env_sync<TPE>(mask);
         } else if (args.illegal) {
@@ -1372,7 +2038,15 @@ extern "C" int ppn_launch_step(const PpnDevCase* c, const PpnDevChronics* ch, co
             if (dims_match<Dims30>(c)) return launch_group<32, 2, Dims30, 5>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
             return launch_group<32, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 256:
-            if (dims_match<Dims118>(c)) return launch_group<256, 8, Dims118, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+            // solve mode (no dense matrices): three CTAs per SM; inverse modes fill the SM's shared memory with one CTA
+            if (dims_match<Dims118>(c)) {
+                if (args->sparse >= 2) {
+                    static const int minb = getenv("PPN_MINB") ? atoi(getenv("PPN_MINB")) : 2;
+                    if (minb == 3) return launch_group<256, 8, Dims118, 3>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+                    if (minb == 2) return launch_group<256, 8, Dims118, 2>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+                }
+                return launch_group<256, 8, Dims118, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+            }
             return launch_group<256, 8, DynDims, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
         default: return (int)cudaErrorInvalidValue;
     }

@@ -12,7 +12,7 @@ for r in rows:
     if r[0] != '':
         try: blocks[-1][1].append((int(r[0]), r[1], int(r[4] or 0), int(r[7] or 0)))
         except Exception: pass
-f, b = blocks[0]
+f, b = max((x for x in blocks if x[0] and x[0].endswith('ppn_kernels.cu')), key=lambda x: len(x[1]), default=blocks[0])
 ts = sum(d[2] for d in b) or 1; ti = sum(d[3] for d in b) or 1
 agg = {}
 for l, s, sm, i in b:

@@ -21,7 +21,7 @@ env = VecRunEnv(case, cfg, chronics, B, reward_constant=float(case.n_sub), therm
 lib = env.lib
 lib.ppn_debug_timing.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
 buf = (ctypes.c_longlong * 64)()
-names = ['start', 'types+scan', 'connectivity', 'entries', 'sbus', 'V0', 'matrices built', 'first mismatch', "B' inverted", "B'' inverted", 'iterations done', 'pfsoln', 'checks']
+names = ['start', 'types+scan', 'connectivity', 'entries', 'sbus', 'V0', 'matrices built', 'first mismatch', "B' inverted (sparse: factor)", "B'' inverted (sparse: inverses)", 'iterations done', 'pfsoln', 'checks']
 for step in range(8):
     torch.cuda.synchronize(); lib.ppn_debug_timing(buf, 1)
     env.step(None, auto_reset=True); torch.cuda.synchronize()
@@ -35,3 +35,5 @@ for step in range(8):
     print('   ' + ', '.join('%s %d' % (names[i + 1], d[i]) for i in range(12)))
     print('   in the loop: P updates %d, Q updates %d, mismatches %d  -> per half-iteration: update %.0f + mismatch %.0f cycles'
           % (buf[21], buf[20], buf[22], (buf[20] + buf[21]) / max(halves, 1), buf[22] / (halves + 1)))
+    if buf[23]:
+        print('   triangular solves %d cycles in total, %.0f per half-iteration' % (buf[23], buf[23] / max(halves, 1)))
