@@ -210,10 +210,12 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     from pypownet_b200.vec_env import VecRunEnv
+    from pypownet_b200 import sharding
     dev = torch.device('cuda', local)
     case, cfg, chronics, imaps = build_workload(args.grid)
     B = args.envs
-    sc, sr = env_starts(B, rank * B)
+    # weak scaling: the global batch of world * B envs is dealt round-robin, rank r owns envs r, r + world, ...
+    sc, sr = sharding.env_starts_of(N_CHRONICS, N_ROWS, sharding.strided_env_ids(B, rank, world))
     env = VecRunEnv(case, cfg, chronics, B, device=local, reward_constant=float(case.n_sub), thermal_limits=imaps,
                     start_chronics=sc, start_rows=sr)
     actions = torch.zeros((B, case.action_length), dtype=torch.uint8, device=dev)      # do-nothing agent
@@ -231,21 +233,37 @@ def run_b200(args):
             bank[k, :, :nt_] = bits * (elem_sub[None, :] == subs[:, None])
             bank[k, np.arange(B), nt_ + rng.integers(0, case.n_line, size=B)] = 1
         action_bank = torch.from_numpy(bank).to(dev)
-    step_counter = [0]
+    step_counter = [0, 0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    from pypownet_b200 import sharding
-    pack = torch.zeros((B, sharding.PACK_WIDTH), dtype=torch.float64, device=dev)
-    gathered = torch.zeros((world * B, sharding.PACK_WIDTH), dtype=torch.float64, device=dev) if world > 1 else None
+    # Sharded runs: the step kernel writes the packed (reward[5], done, flag) rows itself and one NCCL all-gather per
+    # step brings every shard's rows to every rank.  The gather of step t runs on NCCL's stream while step t+1 is
+    # already computing (two pack / result buffers); it is waited for inside the timed interval of step t+1, the last
+    # one before the closing synchronisation, so every collective completes inside the timed region.
+    packs = [torch.zeros((B, sharding.PACK_WIDTH), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    gathered = [torch.zeros((world * B, sharding.PACK_WIDTH), dtype=torch.float64, device=dev) for _ in range(2)] \
+        if world > 1 else None
+    works = [None, None]
 
     def one_step():
         a = actions
         if action_bank is not None:
             a = action_bank[step_counter[0] % 16]
             step_counter[0] += 1
+        if world > 1:
+            buf = step_counter[1] & 1
+            step_counter[1] += 1
+            env.enable_result_pack(packs[buf])
         obs, reward, done, flag = env.step(a, auto_reset=True)
         if world > 1:      # rewards / dones / flags of every shard on every rank (NCCL over NVLink)
-            sharding.gather_results(sharding.pack_results(reward, done, flag, out=pack), world, out=gathered)
+            if works[buf ^ 1] is not None:
+                works[buf ^ 1].wait()          # the previous step's gather (stream wait, not a host block)
+            works[buf] = dist.all_gather_into_tensor(gathered[buf], packs[buf], async_op=True)
         return done
+
+    def drain():
+        for w in works:
+            if w is not None:
+                w.wait()
 
     for _ in range(max(args.warmup, 3)):
         one_step()
@@ -264,6 +282,8 @@ def run_b200(args):
     for k in range(args.steps):
         ev[k][0].record()
         d = one_step()
+        if k == args.steps - 1:
+            drain()                                      # the last gather also completes inside the timed region
         ev[k][1].record()
         n_done += d.sum()
         flush.fill_(k & 1)                               # evict state/observation/chronics from L2 (126 MB)
@@ -287,6 +307,7 @@ def run_b200(args):
     a0.record()
     for _ in range(args.steps):
         one_step()
+    drain()
     a1.record()
     torch.cuda.synchronize()
     warm_value = world * B * args.steps / (a0.elapsed_time(a1) * 1e-3)

@@ -151,6 +151,11 @@ int ppn_process_game_over(ppn_env* env, const uint8_t* mask_dev, double* obs_dev
 /* Game.is_action_valid (game.py:755-760): valid_dev uint8 [n_envs]. */
 int ppn_action_valid(ppn_env* env, const uint8_t* act_dev, uint8_t* valid_dev, void* stream);
 
+/* Optional: every following ppn_step also writes one packed row per env, reward[5] | done | flag as 7 doubles, into
+ * pack_dev [n_envs][7] (device memory, caller-owned; NULL switches it off).  It is the row an env-sharded run gathers
+ * over NCCL each step: written by the step kernel itself, no packing kernels between step and collective. */
+int ppn_set_result_pack(ppn_env* env, double* pack_dev);
+
 /* Host-buffer form of ppn_step (what a host-side agent calls, RunEnv.step semantics, environment.py:848-866): the batch
  * is cut into chunks, each chunk runs  actions H2D -> step kernel -> results D2H  on its own stream so that copies overlap
  * the kernels of the other chunks; returns when every result is in the host buffers.  Page-locked buffers

@@ -36,6 +36,7 @@ struct ppn_env {
     int sp_blob_dbl[2] = {0, 0};   // doubles of their index tables
     int sparse = 0;            // solver mode of PpnStepArgs.sparse
     int alt_sparse = 0, alt_mat_cap = 0, alt_env_smem_bytes = 0;   // plan used once the handle has seen actions
+    double* pack_dev = nullptr;   // optional packed result rows written by ppn_step (ppn_set_result_pack)
     int* h_split = nullptr;    // page-locked, mapped: the kernel sets it when an env applies a node switch
     int* d_split = nullptr;    // its device alias
     long long ws_dense = 0;
@@ -620,7 +621,14 @@ extern "C" int ppn_step(ppn_env* env, const uint8_t* act_dev, double* obs_dev, i
     PpnStepArgs a{};
     a.mode = PPN_MODE_STEP; a.auto_reset = auto_reset; a.act = act_dev;
     a.obs = obs_dev; a.obs_stride = obs_stride; a.reward = reward_dev; a.done = done_dev; a.flag = flag_dev; a.illegal = illegal_dev;
+    a.pack = env->pack_dev;
     return launch(env, a, (cudaStream_t)stream);
+}
+
+extern "C" int ppn_set_result_pack(ppn_env* env, double* pack_dev) {
+    if (!env) return fail(nullptr, PPN_E_INVALID, "ppn_set_result_pack: null handle");
+    env->pack_dev = pack_dev;
+    return PPN_OK;
 }
 
 extern "C" int ppn_simulate(ppn_env* env, int n_candidates, const uint8_t* act_dev, double* obs_dev, int64_t obs_stride,

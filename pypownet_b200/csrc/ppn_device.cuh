@@ -151,6 +151,7 @@ struct PpnStepArgs {
     uint8_t* done;              // [rows] or NULL
     int32_t* flag;              // [rows] or NULL
     uint8_t* illegal;           // [rows][1+2N+S] or NULL
+    double* pack;               // [rows][7] reward[5] | done | flag as doubles (the row a sharded run all-gathers) or NULL
     double* ws;                 // global workspace for matrices that do not fit the shared-memory budget
     long long ws_stride;        // doubles per env
     long long ws_dense;         // sparse solver: offset of the factor storage inside the env's slice

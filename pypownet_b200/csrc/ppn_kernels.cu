@@ -585,12 +585,14 @@ template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp
                    a_rpack = tb + 4u * sp.o_rpack, a_rowoff = tb + 4u * sp.o_rowoff, a_z = saddr(Z);
     const int r0 = sp.cut_row, nt = sp.nt;
     const int t = tid >> 2, part = tid & 3;
+    const int wrow = (tid >> 5) << 3;   // first row of a pass that falls to this warp (eight rows per warp)
     constexpr int RS = TPE / 4;   // rows per pass
     int s0 = lds32(a_lev + 4u);
     for (int lv = 1; lv < sp.cut_lev; lv++) {   // sparse forward steps (rows of level 0 depend on nothing)
         const int s1 = lds32(a_lev + 4u * (lv + 1));
 #pragma unroll 1
         for (int ib = s0; ib < s1; ib += RS) {
+            if (ib + wrow >= s1) break;   // no row of this pass falls to this warp (warp-uniform)
             const int i = ib + t;
             double y = 0.0;
             if (i < s1) {
@@ -611,7 +613,7 @@ template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp
         s0 = s1;
     }
     // top block: y2 = w2 - L21 y1 (entries below the cut only)
-    {
+    if (wrow < nt) {
         double y = 0.0;
         if (t < nt) {
             const unsigned pk = (unsigned)lds32(a_rowpk + 4u * (r0 + t));
@@ -631,7 +633,7 @@ template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp
     // x2 = Z y2
     {
         double x = 0.0, x2 = 0.0;
-        if (t < nt) {
+        if (wrow < nt && t < nt) {
             const unsigned zr = a_z + 8u * (unsigned)(t * ldz), wr = a_w + 8u * r0;
             int j = part;
 #pragma unroll 1
@@ -644,8 +646,10 @@ template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp
             if (j < nt) x = fma(lds64(zr + 8u * j), lds64(wr + 8u * j), x);
             x += x2;
         }
-        x += __shfl_xor_sync(PPN_FULL, x, 1);
-        x += __shfl_xor_sync(PPN_FULL, x, 2);
+        if (wrow < nt) {
+            x += __shfl_xor_sync(PPN_FULL, x, 1);
+            x += __shfl_xor_sync(PPN_FULL, x, 2);
+        }
         __syncthreads();
         if (t < nt && part == 0) sts64(a_w + 8u * (r0 + t), x);
     }
@@ -655,6 +659,7 @@ template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp
         const int e0 = lds32(a_lev + 4u * lv);
 #pragma unroll 1
         for (int ib = e0; ib < e1; ib += RS) {
+            if (ib + wrow >= e1) break;
             const int i = ib + t;
             double y = 0.0;
             if (i < e1) {
@@ -1936,11 +1941,16 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
             if (tid == 0) {
                 double* r = args.reward + (size_t)slot * 5;
                 r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4;
+                if (args.pack) {
+                    double* q = args.pack + (size_t)slot * 7;
+                    q[0] = r0; q[1] = r1; q[2] = r2; q[3] = r3; q[4] = r4;
+                }
             }
         }
         if (tid == 0) {
             if (args.done) args.done[slot] = done ? 1 : 0;
             if (args.flag) args.flag[slot] = flag;
+            if (args.pack) { args.pack[(size_t)slot * 7 + 5] = done ? 1.0 : 0.0; args.pack[(size_t)slot * 7 + 6] = (double)flag; }
         }
         if (args.illegal && mode != PPN_MODE_INIT) {
             uint8_t* il = args.illegal + (size_t)slot * (1 + 2 * N + S);

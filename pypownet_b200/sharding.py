@@ -22,6 +22,19 @@ def env_starts(n_chronics, n_rows, lo, hi):
     return (e % n_chronics).astype(np.int32), ((e // n_chronics) % max(n_rows - 1, 1)).astype(np.int32)
 
 
+def strided_env_ids(n_envs_per_rank, rank, world_size):
+    """Global env indices of a rank when the batch is dealt round-robin (env e -> GPU e mod n_gpu): every
+    shard then samples the same mix of chronics and rows, so no rank carries a systematically heavier batch -- the
+    step time of a synchronous run is the maximum over ranks."""
+    return rank + world_size * np.arange(int(n_envs_per_rank))
+
+
+def env_starts_of(n_chronics, n_rows, env_ids):
+    """Starting chronic / first row of the given global env indices (same rule as env_starts)."""
+    e = np.asarray(env_ids)
+    return (e % n_chronics).astype(np.int32), ((e // n_chronics) % max(n_rows - 1, 1)).astype(np.int32)
+
+
 def pack_results(reward, done, flag, out=None):
     """[B, 7] float64 rows from reward [B,5] f64, done [B] u8, flag [B] i32 (any device)."""
     B = reward.shape[0]

@@ -145,6 +145,19 @@ class VecRunEnv(object):
                                           1 if auto_reset else 0, self._stream()))
         return self.obs, self.reward, self.done, self.flag
 
+    def enable_result_pack(self, buffer=None):
+        """From now on `step` also fills self.pack [B, 7] float64 = reward[5] | done | flag, written by the step kernel:
+        the row an env-sharded run all-gathers each step (pypownet_b200.sharding.gather_results).  `buffer` switches
+        to a caller-provided tensor (double buffering while a gather of the previous rows is still in flight)."""
+        if buffer is not None:
+            if buffer.dtype != torch.float64 or tuple(buffer.shape) != (self.n_envs, 7) or not buffer.is_contiguous():
+                raise ValueError('result pack must be a contiguous float64 tensor of shape (%d, 7)' % self.n_envs)
+            self.pack = buffer
+        elif getattr(self, 'pack', None) is None:
+            self.pack = torch.zeros((self.n_envs, 7), dtype=torch.float64, device=self.device)
+        self._check(self.lib.ppn_set_result_pack(self.handle, _ptr(self.pack)))
+        return self.pack
+
     def simulate(self, actions, n_candidates=1):
         """RunEnv.simulate for n_candidates actions per env ([B * n_candidates, action_length], env-major), no state
         change.  Returns fresh tensors (obs, reward, done, flag) with B * n_candidates rows."""

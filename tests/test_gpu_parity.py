@@ -113,6 +113,52 @@ def test_step_host_matches_device_entry_point():
         assert np.array_equal(f1.cpu().numpy(), f2)
 
 
+@pytest.mark.parametrize('name,mode', [('d118_ac_random', 0), ('d118_ac_random', 1), ('d118_ac_random', 2),
+                                       ('d118_ac_random', 3), ('d30_ac_random', 0), ('d30_ac_random', 1),
+                                       ('d30_ac_random', 2), ('d14_ac_random', 1), ('d14_dc_random', 1),
+                                       ('d14_dc_random', 2)])
+def test_every_linear_solver_reproduces_the_reference(name, mode, monkeypatch):
+    """The linear algebra behind B' / B'' / Bdc has four implementations (dense Gauss-Jordan inverse, sparse LDL^T +
+    explicit inverses, sparse LDL^T + level-scheduled solves, hybrid sparse / dense top block; PpnStepArgs.sparse);
+    the library picks one per grid size, PPN_SPARSE forces one.  Each must reproduce the reference fixture, including
+    the steps whose node-splitting actions switch the factor to the two-rows-per-substation structure."""
+    monkeypatch.setenv('PPN_SPARSE', str(mode))
+    fx = Fixture(name)
+    B = 2
+    env = vec_env(fx, B)
+    worst = 0.0
+    for t in range(min(len(fx.actions), 40)):
+        obs, reward, done, flag = env.step(np.repeat(fx.actions[t][None], B, axis=0))
+        d, f = done.cpu().numpy(), flag.cpu().numpy()
+        assert np.all(d == int(fx.done[t])) and np.all(f == int(fx.flag[t])), 'step %d: %s %s' % (t, d, f)
+        if fx.done[t]:
+            obs = env.process_game_over(done)
+            expect = fx.reset_obs[t]
+        else:
+            expect = fx.obs[t]
+        got = obs.cpu().numpy()
+        worst = max(worst, float(np.max(np.abs(got[0] - expect))))
+    assert worst < TOL, worst
+
+
+def test_plan_switch_after_node_splitting_keeps_parity():
+    """IEEE-118 handles start on the small hybrid shared-memory plan and move to the explicit-inverse plan once an env
+    has applied a node switch (the kernel raises a flag in page-locked host memory): the trajectory must not notice."""
+    fx = Fixture('d118_ac_random')
+    B = 4
+    env = vec_env(fx, B)
+    c0 = env.counters()
+    worst = 0.0
+    for t in range(len(fx.actions)):
+        obs, reward, done, flag = env.step(np.repeat(fx.actions[t][None], B, axis=0))
+        assert np.all(done.cpu().numpy() == int(fx.done[t])) and np.all(flag.cpu().numpy() == int(fx.flag[t])), t
+        if fx.done[t]:
+            obs = env.process_game_over(done)
+        expect = fx.reset_obs[t] if fx.done[t] else fx.obs[t]
+        worst = max(worst, float(np.max(np.abs(obs.cpu().numpy()[B - 1] - expect))))
+    assert worst < TOL, worst
+
+
 @pytest.mark.parametrize('pinned', [True, False])
 def test_chunked_host_entry_point_is_bit_identical(pinned):
     """ppn_step_host: page-locked result buffers are written by the kernel itself (zero-copy, one launch); pageable ones
@@ -151,6 +197,21 @@ def test_chunked_host_entry_point_is_bit_identical(pinned):
         assert e2.counters()['kernel_launches'] > e1.counters()['kernel_launches']   # one launch per chunk
     else:
         assert e2.counters()['kernel_launches'] == e1.counters()['kernel_launches']  # zero-copy: one launch
+
+
+def test_kernel_written_result_pack_equals_the_three_outputs():
+    """ppn_set_result_pack: the row an env-sharded run all-gathers (reward[5] | done | flag) is written by the step
+    kernel itself and must equal what packing the three output tensors gives."""
+    from pypownet_b200 import sharding
+    fx = Fixture('d14_ac_random')
+    B = 6
+    env = vec_env(fx, B)
+    pack = env.enable_result_pack()
+    for t in range(25):
+        obs, reward, done, flag = env.step(np.repeat(fx.actions[t][None], B, axis=0), auto_reset=True)
+        assert torch.equal(pack, sharding.pack_results(reward, done, flag)), t
+        r, d, f = sharding.unpack_results(pack)
+        assert torch.equal(d, done) and torch.equal(f, flag)
 
 
 def test_is_action_valid_and_illegal_masks():

@@ -69,3 +69,11 @@ def test_gather_of_packed_results_world_size_2():
         assert np.array_equal(r, np.stack([g * k for k in range(1, 6)], axis=1))
         assert np.array_equal(d, (np.arange(n_total) % 3 == 0).astype(np.uint8))
         assert np.array_equal(f, (np.arange(n_total) % 5).astype(np.int32))
+
+
+def test_round_robin_shards_cover_the_global_batch_once():
+    ids = np.concatenate([sharding.strided_env_ids(16, r, 4) for r in range(4)])
+    assert sorted(ids.tolist()) == list(range(64))
+    c, r = sharding.env_starts_of(12, 720, sharding.strided_env_ids(16, 1, 4))
+    c0, r0 = sharding.env_starts(12, 720, 0, 64)
+    assert np.array_equal(c, c0[1::4]) and np.array_equal(r, r0[1::4])
