@@ -92,3 +92,44 @@ class VecRandomSplitAndSwitch(object):
         lines = torch.zeros((B, case.n_line), dtype=torch.uint8, device=dev)
         lines[torch.arange(B, device=dev), line] = 1
         return torch.cat([nodes, lines], dim=1)
+
+
+class VecGreedySearch(object):
+    """Batched GreedySearch (reference: pypownet/agent.py:227-325): a depth-1 tree search that simulates the do-nothing
+    action, every single line-status switch and, for every substation with 4 or 5 elements, every switch pattern of its
+    elements whose first switch is 0, and plays the candidate with the highest summed reward (the first one on ties,
+    as `rewards.index(max(rewards))`).  The reference runs its 1 + N + sum 2^(k-1) simulations one after the other
+    (69 for IEEE-14); here all candidates of all envs are ONE ppn_simulate launch (B x K rows, no state change)."""
+
+    def __init__(self, vec_env):
+        import itertools
+        import torch
+        self.env = vec_env
+        case = vec_env.case
+        A, n_node = case.action_length, case.n_gen + case.n_load + 2 * case.n_line
+        cands = [np.zeros(A, dtype=np.uint8)]
+        for l in range(case.n_line):
+            a = np.zeros(A, dtype=np.uint8)
+            a[n_node + l] = 1
+            cands.append(a)
+        for s in range(case.n_sub):
+            el = np.flatnonzero(case.elem_sub == s)          # productions, loads, line origins, line extremities
+            if 3 < len(el) < 6:
+                for conf in itertools.product([0, 1], repeat=len(el) - 1):
+                    a = np.zeros(A, dtype=np.uint8)
+                    a[el] = (0,) + conf
+                    cands.append(a)
+        self.candidates = torch.from_numpy(np.array(cands)).to(vec_env.device)          # [K, A]
+        self.n_candidates = len(cands)
+        self.last_rewards = None
+
+    def act(self, observations=None):
+        import torch
+        env, K = self.env, self.n_candidates
+        batch = self.candidates.unsqueeze(0).expand(env.n_envs, K, -1).reshape(env.n_envs * K, -1).contiguous()
+        _, reward, done, flag = env.simulate(batch, n_candidates=K)
+        r = reward.view(env.n_envs, K, 5)
+        total = (((r[..., 0] + r[..., 1]) + r[..., 2]) + r[..., 3]) + r[..., 4]       # sum(reward_aslist), same order
+        self.last_rewards, self.last_done, self.last_flag = r, done.view(env.n_envs, K), flag.view(env.n_envs, K)
+        best = torch.argmax((total == total.max(dim=1, keepdim=True).values).to(torch.uint8), dim=1)   # first maximum
+        return self.candidates[best]

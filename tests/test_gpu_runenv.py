@@ -75,3 +75,34 @@ def test_vec_runner_random_agent_runs():
                     thermal_limits=fx.thermal_limits)
     cum, overs = VecRunner(env, VecRandomSplitAndSwitch(env, seed=3)).loop(20)
     assert np.all(np.isfinite(cum.cpu().numpy())) and int(overs.sum().item()) >= 0
+
+
+def test_batched_greedy_search_reproduces_the_reference_agent():
+    """tests/golden/greedy/d14_greedy.npz holds what the reference GreedySearch (agent.py:227-325) simulated on the
+    reference environment: 69 candidate actions per step with their five sub-rewards, the action it chose and the
+    outcome of playing it.  VecGreedySearch evaluates all candidates of all envs in one ppn_simulate launch."""
+    import numpy as np
+    import torch
+    from golden_util import Fixture
+    from pypownet_b200.agent import VecGreedySearch
+    from pypownet_b200.vec_env import VecRunEnv
+    fx = Fixture('greedy/d14_greedy')
+    z = fx.z
+    B = 3
+    env = VecRunEnv(fx.case, fx.config, fx.chronics, B, device=0, game_over_mode=fx.mode,
+                    reward_constant=fx.reward_constant, thermal_limits=fx.thermal_limits)
+    agent = VecGreedySearch(env)
+    assert agent.n_candidates == z['cand_actions'].shape[1]
+    assert np.array_equal(agent.candidates.cpu().numpy(), z['cand_actions'][0])       # same candidates, same order
+    for t in range(len(fx.actions)):
+        a = agent.act()
+        got = agent.last_rewards.cpu().numpy()
+        for e in (0, B - 1):
+            assert np.array_equal(agent.last_done[e].cpu().numpy().astype(bool), z['cand_done'][t])
+            assert np.array_equal(agent.last_flag[e].cpu().numpy(), z['cand_flag'][t])
+            assert np.nanmax(np.abs(got[e] - z['cand_reward'][t])) < 1e-7
+        assert np.array_equal(a.cpu().numpy(), np.repeat(fx.actions[t][None], B, axis=0))
+        obs, reward, done, flag = env.step(a)
+        assert not bool(done.any()) and not fx.done[t]
+        assert np.max(np.abs(obs.cpu().numpy()[0] - fx.obs[t])) < 1e-7
+        assert np.max(np.abs(reward.cpu().numpy() - fx.reward[t][None])) < 1e-7

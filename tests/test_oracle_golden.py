@@ -40,6 +40,25 @@ def test_oracle_reproduces_reference_trajectory(name):
     assert np.max(np.abs(env.observation_static() - fx.obs0[nd:])) == 0
 
 
+def test_oracle_reproduces_what_the_reference_greedy_search_simulated():
+    """tests/golden/greedy/d14_greedy.npz (tools/make_golden_greedy.py): the 69 candidates the unmodified reference
+    GreedySearch agent (agent.py:227-325) simulated per step, their sub-rewards, and the action it played."""
+    fx = Fixture('greedy/d14_greedy')
+    z = fx.z
+    env = make_env(fx)
+    nd = fx.case.obs_dynamic_length
+    for t in range(len(fx.actions)):
+        totals = []
+        for k in range(z['cand_actions'].shape[1]):
+            o, r, d, f, _ = env.simulate(z['cand_actions'][t, k])
+            assert (bool(d), int(f)) == (bool(z['cand_done'][t, k]), int(z['cand_flag'][t, k])), (t, k)
+            assert np.max(np.abs(r - z['cand_reward'][t, k])) < TOL, (t, k)
+            totals.append(sum(r))
+        assert np.array_equal(z['cand_actions'][t, int(np.argmax(totals))], fx.actions[t])
+        o, r, d, f, _ = env.step(fx.actions[t])
+        assert not d and np.max(np.abs(o - fx.obs[t][:nd])) < TOL
+
+
 def test_known_answers_of_the_reference_suite():
     """/root/reference/tests/test_core.py:351-372 (slack production after the load-flow at t=1,2,3, 1e-3 MW) and
     :551-603 (losses), on the reference's own test environment default14_for_tests, do-nothing agent."""
