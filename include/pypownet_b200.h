@@ -151,6 +151,15 @@ int ppn_process_game_over(ppn_env* env, const uint8_t* mask_dev, double* obs_dev
 /* Game.is_action_valid (game.py:755-760): valid_dev uint8 [n_envs]. */
 int ppn_action_valid(ppn_env* env, const uint8_t* act_dev, uint8_t* valid_dev, void* stream);
 
+/* Diagnostic, host only (no GPU): builds the sparse LDL^T tables of a grid (elimination order, fill pattern, per-level
+ * update lists, packed row / column views, sparse / dense cut -- everything the kernels index with) exactly as
+ * ppn_create does, and replays the kernels' factorisation and solves on the host against a dense Gaussian elimination,
+ * on a random symmetric positive definite matrix over a random topology.  full = 0: one row per substation, 1: two
+ * (split buses).  *max_err_out = largest deviation of the solutions; info_out (5 ints or NULL) = rows, off-diagonal
+ * entries of L, levels, first dense level, rows of the dense block.  A check of the tables, not a compute path. */
+int ppn_sparse_selfcheck(int n_sub, int n_line, const int32_t* line_or_sub, const int32_t* line_ex_sub, int full,
+                         uint32_t seed, double* max_err_out, int32_t* info_out);
+
 /* Optional: every following ppn_step also writes one packed row per env, reward[5] | done | flag as 7 doubles, into
  * pack_dev [n_envs][7] (device memory, caller-owned; NULL switches it off).  It is the row an env-sharded run gathers
  * over NCCL each step: written by the step kernel itself, no packing kernels between step and collective. */

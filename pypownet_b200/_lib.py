@@ -77,6 +77,7 @@ SYMBOLS = {
     'ppn_action_valid': (C.c_int, [VP, VP, VP, VP]),
     'ppn_step_host': (C.c_int, [VP, VP, VP, C.c_int64, VP, VP, VP, VP, C.c_int]),
     'ppn_set_result_pack': (C.c_int, [VP, VP]),
+    'ppn_sparse_selfcheck': (C.c_int, [C.c_int, C.c_int, VP, VP, C.c_int, C.c_uint32, VP, VP]),
     'ppn_state_width': (C.c_int, [VP, C.c_int]),
     'ppn_get_state': (C.c_int, [VP, C.c_int, VP, VP]),
     'ppn_set_state': (C.c_int, [VP, C.c_int, VP, VP]),

@@ -229,6 +229,184 @@ static void build_sparse(int S, int N, const int* lor, const int* lex, const std
     build_sparse_ordered(S, N, lor, lex, order2, full, h, lev);
 }
 
+// hybrid cut: the lowest level from which at most cut_rows rows remain (at least one level stays sparse when there is one)
+static int choose_cut(const SparseHost& h) {
+    int cut = h.n_lev > 1 ? 1 : 0;
+    int cut_rows = 28;   // measured best on B200 for IEEE-118 (12 / 20 / 28 / 40 rows: 1.60 / 1.62 / 1.72 / 1.67 M env-steps/s);
+                         // at most 40: hyb_invert2 keeps a 5 x 5 tile per thread on an 8 x 8 thread grid
+    if (const char* v = getenv("PPN_CUT_ROWS")) { cut_rows = atoi(v); if (cut_rows > 40) cut_rows = 40; if (cut_rows < 1) cut_rows = 1; }
+    while (cut < h.n_lev - 1 && h.n - h.lev_rows_ptr[cut] > cut_rows) cut++;
+    return cut;
+}
+
+// Diagnostic (host only, no GPU): builds the sparse tables of a grid exactly as ppn_create does, fills them with a random
+// symmetric positive definite matrix on a random topology (lines off, buses inactive = identity rows, node bits in the
+// F structure) and replays on the host, table by table, what the kernels do -- level factorisation + level-scheduled
+// solve (sp_factor / sp_solve) and the hybrid sparse / dense-top-block factor and solve (hyb_*) -- against a dense
+// Gaussian elimination.  Returns the largest deviation of the two solutions.  This is a check of the TABLES (ordering,
+// fill pattern, update lists, levels, packed row/column views, cut); it is not a compute path of the library.
+extern "C" int ppn_sparse_selfcheck(int n_sub, int n_line, const int32_t* line_or_sub, const int32_t* line_ex_sub, int full,
+                                    uint32_t seed, double* max_err_out, int32_t* info_out /* n, nnz, n_lev, cut_lev, nt or NULL */) {
+    if (n_sub <= 0 || n_line <= 0 || !line_or_sub || !line_ex_sub || !max_err_out) return fail(nullptr, PPN_E_INVALID, "ppn_sparse_selfcheck: bad arguments");
+    const int S = n_sub, N = n_line, NB = 2 * S;
+    SparseHost h;
+    build_sparse(S, N, line_or_sub, line_ex_sub, min_degree_order(S, N, line_or_sub, line_ex_sub), full != 0, h);
+    const int n = h.n, nnz = h.nnz, cut = choose_cut(h), r0 = h.lev_rows_ptr[cut], nt = n - r0, cut_ent = h.colptr[r0];
+    if (info_out) { info_out[0] = n; info_out[1] = nnz; info_out[2] = h.n_lev; info_out[3] = cut; info_out[4] = nt; }
+    uint64_t st = 0x9E3779B97F4A7C15ull ^ seed;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0; };
+    // topology: node bits (F only), line status, active buses
+    std::vector<int> on(N), en(N), stat(N);
+    for (int l = 0; l < N; l++) { on[l] = full ? rnd() < .2 : 0; en[l] = full ? rnd() < .2 : 0; stat[l] = rnd() < .9; }
+    std::vector<char> active(NB, 0);
+    for (int l = 0; l < N; l++) if (stat[l]) { active[line_or_sub[l] + S * on[l]] = 1; active[line_ex_sub[l] + S * en[l]] = 1; }
+    for (int b = 0; b < NB; b++) if (active[b] && rnd() < .05) active[b] = 0;   // reference / PV rows of B''
+    // assemble as the kernels do: off-diagonals at line_pos, diagonals per row; identity rows elsewhere
+    std::vector<double> Lv(nnz, 0.0), dg(n, 1.0), T(nnz, 0.0), dense((size_t)n * n, 0.0), rhs(n, 0.0);
+    for (int i = 0; i < n; i++) dense[(size_t)i * n + i] = 1.0;
+    std::vector<double> diag(NB, 0.0);
+    for (int l = 0; l < N; l++) {
+        if (!stat[l]) continue;
+        const int f = line_or_sub[l] + S * on[l], t = line_ex_sub[l] + S * en[l];
+        const double w = 0.5 + 1.5 * rnd();
+        diag[f] += w; diag[t] += w;
+        if (active[f] && active[t]) {
+            const int pos = h.line_pos[full ? 4 * l + 2 * on[l] + en[l] : l];
+            if (pos < 0) return fail(nullptr, PPN_E_STATE, "ppn_sparse_selfcheck: line without a position in the pattern");
+            Lv[pos] -= w;
+            const int i = h.bus_row[f], j = h.bus_row[t];
+            dense[(size_t)i * n + j] -= w; dense[(size_t)j * n + i] -= w;
+        }
+    }
+    for (int b = 0; b < NB; b++) {
+        const int i = h.bus_row[b];
+        if (i < 0 || !active[b]) continue;
+        dg[i] = diag[b] + 0.01;
+        dense[(size_t)i * n + i] = dg[i];
+        rhs[i] = rnd() - 0.5;
+    }
+    // dense reference solution (Gaussian elimination with partial pivoting)
+    std::vector<double> a = dense, xref = rhs;
+    for (int k = 0; k < n; k++) {
+        int pv = k;
+        for (int i = k + 1; i < n; i++) if (fabs(a[(size_t)i * n + k]) > fabs(a[(size_t)pv * n + k])) pv = i;
+        if (pv != k) { for (int j = 0; j < n; j++) std::swap(a[(size_t)k * n + j], a[(size_t)pv * n + j]); std::swap(xref[k], xref[pv]); }
+        for (int i = k + 1; i < n; i++) {
+            const double m = a[(size_t)i * n + k] / a[(size_t)k * n + k];
+            if (m == 0.0) continue;
+            for (int j = k; j < n; j++) a[(size_t)i * n + j] -= m * a[(size_t)k * n + j];
+            xref[i] -= m * xref[k];
+        }
+    }
+    for (int k = n - 1; k >= 0; k--) {
+        for (int j = k + 1; j < n; j++) xref[k] -= a[(size_t)k * n + j] * xref[j];
+        xref[k] /= a[(size_t)k * n + k];
+    }
+    double err = 0.0;
+    const std::vector<double> Lv0 = Lv, dg0 = dg;
+    auto target = [&](int id, int limit_ent) {   // left-looking gather of one target; terms with entry (j,k) < limit_ent
+        double acc = id < nnz ? Lv[id] : dg[id - nnz];
+        for (int t = h.trip_ptr[id]; t < h.trip_ptr[id + 1]; t++) {
+            const unsigned pk = (unsigned)h.trip[t];
+            if ((int)(pk & 0xffffu) >= limit_ent) break;
+            acc -= T[pk >> 16] * Lv[pk & 0xffffu];
+        }
+        return acc;
+    };
+    auto factor_levels = [&](int upto) {
+        for (int lv = 0; lv < upto; lv++) {
+            for (int q = h.lev_ptr[lv]; q < h.lev_ptr[lv + 1]; q++) {
+                const int id = h.lev_ent[q];
+                const double v = target(id, nnz);
+                if (id < nnz) T[id] = v; else dg[id - nnz] = v;
+            }
+            for (int q = h.lev_ptr[lv]; q < h.lev_ptr[lv + 1]; q++) {
+                const int id = h.lev_ent[q];
+                if (id < nnz) Lv[id] = T[id] / dg[h.ecol[id]];
+            }
+        }
+    };
+    {   // (1) full level factorisation, level-scheduled solve through the packed row / column views
+        factor_levels(h.n_lev);
+        std::vector<double> w = rhs;
+        for (int lv = 1; lv < h.n_lev; lv++)
+            for (int i = h.lev_rows_ptr[lv]; i < h.lev_rows_ptr[lv + 1]; i++) {
+                const unsigned pk = (unsigned)h.rowpk[i];
+                double acc = w[i];
+                for (unsigned t = pk >> 8, c = 0; c < (pk & 255u); c++, t++) {
+                    const unsigned p0 = (unsigned)h.rpack[t];
+                    acc -= Lv[(p0 >> 16) / 8] * w[(p0 & 0xffffu) / 8];
+                }
+                w[i] = acc;
+            }
+        for (int lv = h.n_lev - 1; lv >= 0; lv--)
+            for (int i = h.lev_rows_ptr[lv]; i < h.lev_rows_ptr[lv + 1]; i++) {
+                const unsigned pk = (unsigned)h.colpk[i];
+                double acc = w[i] / dg[i];
+                for (unsigned e2 = pk >> 8, c = 0; c < (pk & 255u); c++, e2++) acc -= Lv[e2] * w[h.rowoff[e2] / 8];
+                w[i] = acc;
+            }
+        for (int i = 0; i < n; i++) err = fmax(err, fabs(w[i] - xref[i]));
+    }
+    {   // (2) hybrid: sparse levels below the cut, Schur complement of the top block, its dense inverse
+        Lv = Lv0; dg = dg0; std::fill(T.begin(), T.end(), 0.0);
+        factor_levels(cut);
+        std::vector<double> Z((size_t)nt * nt, 0.0);
+        for (int q = h.lev_ptr[cut]; q < h.lev_ptr[h.n_lev]; q++) {
+            const int id = h.lev_ent[q];
+            const int i = id < nnz ? h.rowidx[id] : id - nnz, j = id < nnz ? h.ecol[id] : id - nnz;
+            const double v = target(id, cut_ent);
+            Z[(size_t)(i - r0) * nt + (j - r0)] = v; Z[(size_t)(j - r0) * nt + (i - r0)] = v;
+        }
+        for (int k = 0; k < nt; k++) {   // Gauss-Jordan without pivoting, as hyb_invert2
+            const double p = 1.0 / Z[(size_t)k * nt + k];
+            for (int i = 0; i < nt; i++) {
+                if (i == k) continue;
+                const double ci = Z[(size_t)i * nt + k] * p;
+                for (int j = 0; j < nt; j++) if (j != k) Z[(size_t)i * nt + j] -= ci * Z[(size_t)k * nt + j];
+                Z[(size_t)i * nt + k] = -ci;
+            }
+            for (int j = 0; j < nt; j++) Z[(size_t)k * nt + j] = j == k ? p : Z[(size_t)k * nt + j] * p;
+        }
+        std::vector<double> w = rhs;
+        for (int lv = 1; lv < cut; lv++)
+            for (int i = h.lev_rows_ptr[lv]; i < h.lev_rows_ptr[lv + 1]; i++) {
+                const unsigned pk = (unsigned)h.rowpk[i];
+                double acc = w[i];
+                for (unsigned t = pk >> 8, c = 0; c < (pk & 255u); c++, t++) {
+                    const unsigned p0 = (unsigned)h.rpack[t];
+                    acc -= Lv[(p0 >> 16) / 8] * w[(p0 & 0xffffu) / 8];
+                }
+                w[i] = acc;
+            }
+        std::vector<double> y2(nt);
+        for (int t = 0; t < nt; t++) {
+            const unsigned pk = (unsigned)h.rowpk[r0 + t];
+            double acc = w[r0 + t];
+            for (unsigned q = pk >> 8, c = 0; c < (pk & 255u); c++, q++) {
+                const unsigned p0 = (unsigned)h.rpack[q];
+                if ((p0 & 0xffffu) < 8u * (unsigned)r0) acc -= Lv[(p0 >> 16) / 8] * w[(p0 & 0xffffu) / 8];
+            }
+            y2[t] = acc;
+        }
+        for (int t = 0; t < nt; t++) {
+            double x = 0.0;
+            for (int j = 0; j < nt; j++) x += Z[(size_t)t * nt + j] * y2[j];
+            w[r0 + t] = x;
+        }
+        for (int lv = cut - 1; lv >= 0; lv--)
+            for (int i = h.lev_rows_ptr[lv]; i < h.lev_rows_ptr[lv + 1]; i++) {
+                const unsigned pk = (unsigned)h.colpk[i];
+                double acc = w[i] / dg[i];
+                for (unsigned e2 = pk >> 8, c = 0; c < (pk & 255u); c++, e2++) acc -= Lv[e2] * w[h.rowoff[e2] / 8];
+                w[i] = acc;
+            }
+        for (int i = 0; i < n; i++) err = fmax(err, fabs(w[i] - xref[i]));
+    }
+    *max_err_out = err;
+    return PPN_OK;
+}
+
 extern "C" const char* ppn_build_info(void) {
     return "pypownet_b200 step path; sm_100a; fused warp/CTA-per-env fast-decoupled XB + DC load-flow; built " __DATE__;
 }
@@ -329,12 +507,7 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
             if (h.nnz >= 8192 || 8 * h.n >= 32768) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "ppn_create: grid too large for the sparse factor tables"); }
             PpnDevSparse& d = c.sp[f];
             d.n = h.n; d.nnz = h.nnz; d.n_lev = h.n_lev;
-            // hybrid cut: the lowest level from which at most 40 rows remain (at least one level stays sparse when there is one)
-            int cut = h.n_lev > 1 ? 1 : 0;
-            int cut_rows = 28;   // measured best on B200 for IEEE-118 (12 / 20 / 28 / 40 rows: 1.60 / 1.62 / 1.72 / 1.67 M env-steps/s);
-                                 // at most 40: hyb_invert2 keeps a 5 x 5 tile per thread on an 8 x 8 thread grid
-            if (const char* v = getenv("PPN_CUT_ROWS")) { cut_rows = atoi(v); if (cut_rows > 40) cut_rows = 40; if (cut_rows < 1) cut_rows = 1; }
-            while (cut < h.n_lev - 1 && h.n - h.lev_rows_ptr[cut] > cut_rows) cut++;
+            const int cut = choose_cut(h);
             d.cut_lev = cut; d.cut_row = h.lev_rows_ptr[cut]; d.cut_ent = h.colptr[d.cut_row]; d.nt = h.n - d.cut_row;
             std::vector<int> blob;
             auto put_i = [&](const std::vector<int>& v) { const int o = (int)blob.size(); blob.insert(blob.end(), v.begin(), v.end()); return o; };
@@ -417,6 +590,7 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     env->ws_dense = 2LL * NB * (NB | 1);
     const int worst = (int)env->ws_dense + env->sp_need[1] + env->sp_blob_dbl[1];
     env->envs_per_block = tpe == 16 ? 4 : (tpe == 32 ? 2 : 1);   // 64-thread CTAs for the sub-warp / warp kernels
+    if (const char* v = getenv("PPN_EPB")) { if (tpe == 32 && atoi(v) >= 1 && atoi(v) <= 2) env->envs_per_block = atoi(v); }
     const int cap_bytes = max_smem / env->envs_per_block - fixed - 64;
     if (cap_bytes < 0) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "grid too large for the shared-memory plan"); }
     // doubles of shared memory per env for matrices / factors / tables under a given solver mode
