@@ -92,7 +92,7 @@ typedef struct ppn_config {
     int32_t pf_max_it;                   /* 25    (grid.py:63) */
     double reward_constant;              /* `constant` of the shipped CustomRewardSignal (14 / 30 / 118) */
     uint64_t seed;                       /* loop_mode 1 only */
-    int32_t threads_per_env;             /* 0 = automatic (half a warp per env up to 16 substations, a warp up to 32, else one CTA of 256); 16, 32 or 256 */
+    int32_t threads_per_env;             /* 0 = automatic (one warp per env up to 32 substations, else one CTA of 128 threads); 16, 32, 128 or 256 */
 } ppn_config;
 
 /* One chronic (chronic.py:174-246): float32 tables with n_rows rows, planned tables ALREADY shifted by one row. */

@@ -35,7 +35,7 @@ struct ppn_env {
     int sp_need[2] = {0, 0};   // doubles of factor storage (both matrices) of the U / F sparse structures
     int sp_blob_dbl[2] = {0, 0};   // doubles of their index tables
     int sparse = 0;            // solver mode of PpnStepArgs.sparse
-    int alt_sparse = 0, alt_mat_cap = 0, alt_env_smem_bytes = 0;   // plan used once the handle has seen actions
+    int alt_sparse = 0, alt_mat_cap = 0, alt_env_smem_bytes = 0, alt_tpe = 0;   // plan used once buses may be split
     double* pack_dev = nullptr;   // optional packed result rows written by ppn_step (ppn_set_result_pack)
     int* h_split = nullptr;    // page-locked, mapped: the kernel sets it when an env applies a node switch
     int* d_split = nullptr;    // its device alias
@@ -230,10 +230,11 @@ static void build_sparse(int S, int N, const int* lor, const int* lex, const std
 }
 
 // hybrid cut: the lowest level from which at most cut_rows rows remain (at least one level stays sparse when there is one)
-static int choose_cut(const SparseHost& h) {
+static int choose_cut(const SparseHost& h, int cut_rows = 20) {
+    // cut_rows: measured on B200 for IEEE-118 -- 256-thread CTAs, two per SM: 12 / 20 / 28 / 40 rows give 1.60 / 1.62 /
+    // 1.72 / 1.67 M env-steps/s; 128-thread CTAs, three per SM (the default): 12 / 20 rows give 1.99 / 2.14 M (28 rows
+    // no longer fit three CTAs).  At most 40: hyb_invert2 keeps a 5 x 5 tile per thread on an 8 x 8 thread grid.
     int cut = h.n_lev > 1 ? 1 : 0;
-    int cut_rows = 28;   // measured best on B200 for IEEE-118 (12 / 20 / 28 / 40 rows: 1.60 / 1.62 / 1.72 / 1.67 M env-steps/s);
-                         // at most 40: hyb_invert2 keeps a 5 x 5 tile per thread on an 8 x 8 thread grid
     if (const char* v = getenv("PPN_CUT_ROWS")) { cut_rows = atoi(v); if (cut_rows > 40) cut_rows = 40; if (cut_rows < 1) cut_rows = 1; }
     while (cut < h.n_lev - 1 && h.n - h.lev_rows_ptr[cut] > cut_rows) cut++;
     return cut;
@@ -569,8 +570,11 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
 
     // ---- threads per env and shared-memory plan
     int tpe = cfg->threads_per_env;
-    if (tpe == 0) tpe = (NB <= 64) ? 32 : 256;   // measured on B200: a full warp per env beats two envs per warp
-    if (tpe != 16 && tpe != 32 && tpe != 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env must be 0, 16, 32 or 256"); }
+    // measured on B200: a full warp per env beats two envs per warp; CTA-per-env grids run 128-thread CTAs (two buses
+    // per thread, three CTAs per SM: IEEE-118 2.14 M env-steps/s against 1.72 M with 256-thread CTAs, two per SM)
+    if (tpe == 0) tpe = (NB <= 64) ? 32 : 128;
+    if (const char* v = getenv("PPN_TPE")) { if (NB > 64 && (atoi(v) == 128 || atoi(v) == 256)) tpe = atoi(v); }
+    if (tpe != 16 && tpe != 32 && tpe != 128 && tpe != 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env must be 0, 16, 32, 128 or 256"); }
     if ((tpe == 16 && NB > 32) || (tpe == 32 && NB > 64) || NB > 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env too small for this grid (16: <= 16 substations, 32: <= 32, 256: <= 128)"); }
     env->tpe = tpe;
     const int fixed = ppn_env_smem_fixed_bytes(S, G, L, N, tpe);
@@ -585,7 +589,7 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     //                                      also the CTA-per-env plan once a handle has received topology actions
     //   3 hybrid sparse / dense top block  CTA per env (IEEE-118): 4.7x the dense 117^3 inverse, two CTAs per SM
     //   (2 = sparse LDL^T with level-scheduled triangular solves: correct but latency-bound, kept for reference)
-    env->sparse = tpe == 256 ? 3 : (tpe == 32 && S > 16 ? 1 : 0);
+    env->sparse = tpe >= 128 ? 3 : (tpe == 32 && S > 16 ? 1 : 0);
     if (const char* v = getenv("PPN_SPARSE")) env->sparse = atoi(v);
     env->ws_dense = 2LL * NB * (NB | 1);
     const int worst = (int)env->ws_dense + env->sp_need[1] + env->sp_blob_dbl[1];
@@ -613,8 +617,17 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     // the F structure does not fit the small hybrid plan, explicit inverses with the whole SM's shared memory do better
     // there (IEEE-118, random node-splitting agent: 0.56 M env-steps/s against 0.24 M).
     env->alt_sparse = env->sparse; env->alt_mat_cap = env->mat_cap; env->alt_env_smem_bytes = env->env_smem_bytes;
-    if (tpe == 256 && env->sparse >= 2 && !getenv("PPN_NO_ALT_PLAN")) {
-        env->alt_sparse = 1; env->alt_mat_cap = plan(1); env->alt_env_smem_bytes = fixed + env->alt_mat_cap * 8;
+    env->alt_tpe = tpe;
+    if (tpe >= 128 && env->sparse >= 2 && !getenv("PPN_NO_ALT_PLAN")) {
+        // explicit inverses want one thread per column: 256-thread CTAs (the per-env state in HBM does not depend on
+        // the thread count; only the reduction scratch of the shared-memory image does)
+        const int fixed_b = ppn_env_smem_fixed_bytes(S, G, L, N, 256);
+        env->alt_tpe = 256;
+        env->alt_sparse = 1;
+        int cap_b = (max_smem - fixed_b - 64) / 8;
+        if (cap_b > worst) cap_b = worst;
+        env->alt_mat_cap = cap_b & ~1;
+        env->alt_env_smem_bytes = fixed_b + env->alt_mat_cap * 8;
     }
     env->ws_stride = worst;
     env->ws_rows = n_envs;
@@ -746,7 +759,7 @@ static int launch(ppn_env* env, PpnStepArgs& a, cudaStream_t s) {
             a.ws = nws;
         }
     }
-    int rc = ppn_launch_step(&env->dc, &env->dch, &env->dcfg, &env->st, &a, env->tpe, env->envs_per_block, smem_bytes, s);
+    int rc = ppn_launch_step(&env->dc, &env->dch, &env->dcfg, &env->st, &a, alt ? env->alt_tpe : env->tpe, env->envs_per_block, smem_bytes, s);
     env->launches++;
     env->async_pending = true;
     if (rc != 0) return fail(env, PPN_E_CUDA, std::string("step kernel launch: ") + cudaGetErrorString((cudaError_t)rc));

@@ -1132,7 +1132,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
     // unit phasor, injections, Ybus diagonal and list position stay in registers for the whole iteration; only
     // the rectangular voltages (read by neighbours) and the mismatch vectors (read by the solves) go through
     // shared memory.
-    constexpr int RB = TPE > 32 ? 1 : (D::NB_MAX > 0 ? (D::NB_MAX + TPE - 1) / TPE : 2);
+    constexpr int RB = D::NB_MAX > 0 ? (D::NB_MAX + TPE - 1) / TPE : (TPE == 256 ? 1 : 2);   // <= 256 buses (CTA), <= 64 (warp)
     double r_vm[RB], r_rvm[RB], r_va[RB], r_cs[RB], r_sn[RB], r_pin[RB], r_qin[RB], r_ydr[RB], r_ydi[RB], r_sr[RB], r_si[RB];
     int r_t[RB], r_ip[RB], r_iq[RB], r_deg[RB], r_k0[RB], r_step[RB];
     // solve mode: the mismatch vectors are indexed by factor row (zero on the identity rows) and are solved in place
@@ -2047,6 +2047,13 @@ extern "C" int ppn_launch_step(const PpnDevCase* c, const PpnDevChronics* ch, co
             }
             if (dims_match<Dims30>(c)) return launch_group<32, 2, Dims30, 5>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
             return launch_group<32, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+        case 128:   // half-size CTAs for the CTA-per-env grids: two buses per thread, the full register file for two CTAs per SM
+            if (dims_match<Dims118>(c)) {
+                static const int minb128 = getenv("PPN_MINB") ? atoi(getenv("PPN_MINB")) : 3;
+                if (minb128 == 3) return launch_group<128, 8, Dims118, 3>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+                return launch_group<128, 8, Dims118, 2>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+            }
+            return launch_group<128, 8, DynDims, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
         case 256:
             // solve mode (no dense matrices): three CTAs per SM; inverse modes fill the SM's shared memory with one CTA
             if (dims_match<Dims118>(c)) {
