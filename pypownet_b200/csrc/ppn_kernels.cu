@@ -1028,9 +1028,11 @@ __device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, do
     const unsigned mask = e.mask;
     bool success;
     // ================= rundcpf: B theta = Pbus on pv+pq, Vm := 1
-    SpFactor f1{};
+    SpFactor f1{}, f2{};
     if (sp) { f1 = sp_carve(spb, *sp, 0); sp_clear<TPE>(*sp, f1, n1, tid); }
     else for (int i = tid; i < n1 * ld1; i += TPE) M1[i] = 0.0;
+    // the hybrid routines always work on two matrices side by side: the second one is an identity here
+    if (sp && solve_mode && TPE > 32 && sp->hyb) { f2 = sp_carve(spb, *sp, 1); sp_clear<TPE>(*sp, f2, n1, tid); }
     if (solve_mode) for (int i = tid; i < NB; i += TPE) e.ydr()[i] = 0.0;   // right-hand side by row (ydr is free in DC mode)
     env_sync<TPE>(mask);
     const double va_ref = e.va()[ref] * (PPN_PI / 180.0);
@@ -1060,9 +1062,8 @@ __device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, do
     if (solve_mode && TPE > 32 && sp->hyb) {
         const int ldz = sp->d->nt | 1;
         double* Z1 = spb + 2 * ppn_sp_factor_doubles(sp->n, sp->nnz);
-        const SpsFactor s1{saddr(f1.T), saddr(f1.Lv), saddr(f1.dg)};
-        // both halves of the CTA factor the same matrix into the same places (identical values): keeps one code path
-        hyb_factor2<TPE>(*sp->d, sp->tb, s1, s1, Z1, Z1, ldz, tid);
+        const SpsFactor s1{saddr(f1.T), saddr(f1.Lv), saddr(f1.dg)}, s2{saddr(f2.T), saddr(f2.Lv), saddr(f2.dg)};
+        hyb_factor2<TPE>(*sp->d, sp->tb, s1, s2, Z1, Z1 + sp->d->nt * ldz, ldz, tid);
         hyb_invert2<TPE>(Z1, Z1 + sp->d->nt * ldz, sp->d->nt, ldz, e.vr(), tid);   // vr | vi: 2 NB doubles of scratch in DC mode
         hyb_solve<TPE>(*sp->d, sp->tb, s1.Lv, s1.dg, Z1, ldz, saddr(e.ydr()), tid);
         for (int i = tid; i < n1; i += TPE) e.Q()[i] = e.ydr()[sp->bus_row[e.busp()[i]]];

@@ -55,10 +55,14 @@ def test_cuda_reproduces_reference_fixture(name):
 
 
 @pytest.mark.parametrize('name,steps', [('d14_ac_random', 120), ('d30_ac_random', 60), ('d118_ac_random', 25),
-                                        ('d14_dc_random', 60)])
+                                        ('d14_dc_random', 60), ('d118_ac_random:DC', 20), ('d30_ac_random:DC', 30)])
 def test_cuda_matches_oracle_on_a_ragged_batch(name, steps):
-    """Envs start on different chronics and rows and receive different random actions; auto-reset as Runner does."""
+    """Envs start on different chronics and rows and receive different random actions; auto-reset as Runner does.
+    `:DC` replays a grid's fixture data with loadflow_mode DC (rundcpf through the same sparse / hybrid solvers)."""
+    name, _, mode = name.partition(':')
     fx = Fixture(name)
+    if mode == 'DC':
+        fx.config = dict(fx.config, loadflow_mode='DC')
     B = 24
     rng = np.random.default_rng(11)
     nch = len(fx.chronics)
