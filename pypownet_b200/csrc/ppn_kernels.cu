@@ -2040,12 +2040,10 @@ extern "C" int ppn_launch_step(const PpnDevCase* c, const PpnDevChronics* ch, co
             return launch_group<16, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 32:
             // IEEE-14: 14 two-env CTAs per SM = 28 envs/SM, so that 4096 envs are one wave on 148 SMs
-            if (dims_match<Dims14>(c)) {
-                static const int variant = getenv("PPN_VARIANT") ? atoi(getenv("PPN_VARIANT")) : 0;
-                if (variant == 1) return launch_group<32, 2, Dims14, 12>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
-                if (variant == 2) return launch_group<32, 2, Dims14, 14>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
-                return launch_group<32, 2, Dims14, 10>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
-            }
+            // IEEE-14: 96 registers, ten 64-thread CTAs per SM.  Measured alternatives: 80 registers (12 CTAs) 9.9 M
+            // env-steps/s, 72 registers (14 CTAs, 4096 envs in one wave) 9.2 M, against 10.9 M -- the spills cost more
+            // than the second wave
+            if (dims_match<Dims14>(c)) return launch_group<32, 2, Dims14, 10>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
             if (dims_match<Dims30>(c)) return launch_group<32, 2, Dims30, 5>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
             return launch_group<32, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 128:   // half-size CTAs for the CTA-per-env grids: two buses per thread, the full register file for two CTAs per SM
