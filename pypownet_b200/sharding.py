@@ -60,3 +60,46 @@ def gather_results(packed, world_size=None, out=None):
         out = torch.empty((world_size * packed.shape[0], packed.shape[1]), dtype=packed.dtype, device=packed.device)
     dist.all_gather_into_tensor(out, packed.contiguous())
     return out
+
+
+class PipelinedGather(object):
+    """One all-gather per step whose communication overlaps the next step: step t writes its packed rows into buffer
+    t mod 2 and starts the gather asynchronously; the gather of step t-1 is waited for right after step t has been
+    enqueued (a stream wait on GPUs), so a buffer is never rewritten while its gather is in flight.  `wait_all` before
+    reading the last results.  bench.py's sharded loop follows the same discipline over NCCL (the two pack buffers are
+    registered with the handle through ppn_set_result_pack); tests/test_sharding_gloo.py covers it on gloo."""
+
+    def __init__(self, n_local, world_size, device='cpu'):
+        self.world = int(world_size)
+        self.packs = [torch.zeros((n_local, PACK_WIDTH), dtype=torch.float64, device=device) for _ in range(2)]
+        self.gathered = [torch.zeros((self.world * n_local, PACK_WIDTH), dtype=torch.float64, device=device)
+                         for _ in range(2)]
+        self.works = [None, None]
+        self.step = 0
+
+    def buffer(self):
+        """The pack buffer the step about to run must fill."""
+        return self.packs[self.step & 1]
+
+    def launch(self):
+        """Call once the step that fills `buffer()` has been enqueued.  Returns the gathered rows of the PREVIOUS step
+        (complete), or None on the first call."""
+        buf = self.step & 1
+        prev = None
+        if self.works[buf ^ 1] is not None:
+            self.works[buf ^ 1].wait()
+            self.works[buf ^ 1] = None
+            prev = self.gathered[buf ^ 1]
+        if self.world > 1:
+            self.works[buf] = dist.all_gather_into_tensor(self.gathered[buf], self.packs[buf], async_op=True)
+        else:
+            self.gathered[buf].copy_(self.packs[buf])
+        self.step += 1
+        return prev
+
+    def wait_all(self):
+        for k in (0, 1):
+            if self.works[k] is not None:
+                self.works[k].wait()
+                self.works[k] = None
+        return self.gathered[(self.step - 1) & 1] if self.step else None

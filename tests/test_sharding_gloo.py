@@ -77,3 +77,42 @@ def test_round_robin_shards_cover_the_global_batch_once():
     c, r = sharding.env_starts_of(12, 720, sharding.strided_env_ids(16, 1, 4))
     c0, r0 = sharding.env_starts(12, 720, 0, 64)
     assert np.array_equal(c, c0[1::4]) and np.array_equal(r, r0[1::4])
+
+
+def _pipeline_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    B = 5
+    pg = sharding.PipelinedGather(B, world)
+    seen = []
+    for t in range(7):
+        pg.buffer().copy_(torch.full((B, sharding.PACK_WIDTH), float(100 * t + rank), dtype=torch.float64))   # "step t"
+        prev = pg.launch()
+        if prev is not None:
+            seen.append(prev.clone())
+    seen.append(pg.wait_all().clone())
+    q.put((rank, [s.numpy() for s in seen]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_gather_delivers_every_step_in_order():
+    """The double-buffered, asynchronous all-gather of bench.py's sharded loop: every step's rows of every rank arrive,
+    in step order, and no buffer is overwritten while its gather is in flight."""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, seen in res:
+        assert len(seen) == 7
+        for t, g in enumerate(seen):
+            assert g.shape == (world * 5, sharding.PACK_WIDTH)
+            for r in range(world):
+                assert np.all(g[5 * r:5 * (r + 1)] == 100 * t + r), (rank, t, r)
