@@ -2028,42 +2028,59 @@ extern "C" int ppn_debug_timing(long long* out_host, int reset) {
 #endif
 
 // -------------------------------------------------------------------------------------------------- launch wrapper
-// tpe: 16 (<= 16 substations), 32 (<= 32 substations) or 256 (one CTA per env, <= 128 substations).  The three IEEE
-// families run kernels specialised on their sizes; any other grid runs the size-generic instantiation.
+// tpe: 16 (<= 16 substations), 32 (<= 32 substations), 128 or 256 (one CTA per env, <= 128 substations).  The three
+// IEEE families run kernels specialised on their sizes; any other grid runs the size-generic instantiation.
+// The file can be compiled in parts so that the build runs in parallel (__graft_entry__.build): -DPPN_PART=0 holds the
+// warp-per-env kernels and the dispatcher, 1 the 128-thread CTA kernels, 2 the 256-thread ones; without PPN_PART
+// everything lands in one translation unit.
+extern "C" int ppn_launch_step_cta128(const PpnDevCase* c, const PpnDevChronics* ch, const PpnDevCfg* cfg, const PpnDevState* st,
+                                      const PpnStepArgs* args, int env_smem_bytes, cudaStream_t stream);
+extern "C" int ppn_launch_step_cta256(const PpnDevCase* c, const PpnDevChronics* ch, const PpnDevCfg* cfg, const PpnDevState* st,
+                                      const PpnStepArgs* args, int env_smem_bytes, cudaStream_t stream);
+
+#if !defined(PPN_PART) || PPN_PART == 0
 extern "C" int ppn_launch_step(const PpnDevCase* c, const PpnDevChronics* ch, const PpnDevCfg* cfg, const PpnDevState* st,
                                const PpnStepArgs* args, int tpe, int envs_per_block, int env_smem_bytes,
                                cudaStream_t stream) {
     if (args->n_envs * args->n_cand <= 0) return 0;
     switch (tpe) {
-        case 16:
-            if (dims_match<Dims14>(c)) return launch_group<16, 2, Dims14, 8>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
+        case 16:   // two envs per warp: measured slower than a warp per env, kept size-generic only
             return launch_group<16, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 32:
-            // IEEE-14: 14 two-env CTAs per SM = 28 envs/SM, so that 4096 envs are one wave on 148 SMs
             // IEEE-14: 96 registers, ten 64-thread CTAs per SM.  Measured alternatives: 80 registers (12 CTAs) 9.9 M
             // env-steps/s, 72 registers (14 CTAs, 4096 envs in one wave) 9.2 M, against 10.9 M -- the spills cost more
             // than the second wave
             if (dims_match<Dims14>(c)) return launch_group<32, 2, Dims14, 10>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
             if (dims_match<Dims30>(c)) return launch_group<32, 2, Dims30, 5>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
             return launch_group<32, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
-        case 128:   // half-size CTAs for the CTA-per-env grids: two buses per thread, the full register file for two CTAs per SM
-            if (dims_match<Dims118>(c)) {
-                static const int minb128 = getenv("PPN_MINB") ? atoi(getenv("PPN_MINB")) : 3;
-                if (minb128 == 3) return launch_group<128, 8, Dims118, 3>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
-                return launch_group<128, 8, Dims118, 2>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
-            }
-            return launch_group<128, 8, DynDims, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
-        case 256:
-            // solve mode (no dense matrices): three CTAs per SM; inverse modes fill the SM's shared memory with one CTA
-            if (dims_match<Dims118>(c)) {
-                if (args->sparse >= 2) {
-                    static const int minb = getenv("PPN_MINB") ? atoi(getenv("PPN_MINB")) : 2;
-                    if (minb == 3) return launch_group<256, 8, Dims118, 3>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
-                    if (minb == 2) return launch_group<256, 8, Dims118, 2>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
-                }
-                return launch_group<256, 8, Dims118, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
-            }
-            return launch_group<256, 8, DynDims, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+        case 128: return ppn_launch_step_cta128(c, ch, cfg, st, args, env_smem_bytes, stream);
+        case 256: return ppn_launch_step_cta256(c, ch, cfg, st, args, env_smem_bytes, stream);
         default: return (int)cudaErrorInvalidValue;
     }
 }
+#endif
+
+#if !defined(PPN_PART) || PPN_PART == 1
+// half-size CTAs for the CTA-per-env grids: two buses per thread, three CTAs per SM (PPN_MINB=2: two, 255 registers)
+extern "C" int ppn_launch_step_cta128(const PpnDevCase* c, const PpnDevChronics* ch, const PpnDevCfg* cfg, const PpnDevState* st,
+                                      const PpnStepArgs* args, int env_smem_bytes, cudaStream_t stream) {
+    if (dims_match<Dims118>(c)) {
+        static const int minb128 = getenv("PPN_MINB") ? atoi(getenv("PPN_MINB")) : 3;
+        if (minb128 == 2) return launch_group<128, 8, Dims118, 2>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+        return launch_group<128, 8, Dims118, 3>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+    }
+    return launch_group<128, 8, DynDims, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+}
+#endif
+
+#if !defined(PPN_PART) || PPN_PART == 2
+// 256-thread CTAs: the explicit-inverse plan (whole SM per CTA) and, with PPN_TPE=256, the hybrid plan at two CTAs per SM
+extern "C" int ppn_launch_step_cta256(const PpnDevCase* c, const PpnDevChronics* ch, const PpnDevCfg* cfg, const PpnDevState* st,
+                                      const PpnStepArgs* args, int env_smem_bytes, cudaStream_t stream) {
+    if (dims_match<Dims118>(c)) {
+        if (args->sparse >= 2) return launch_group<256, 8, Dims118, 2>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+        return launch_group<256, 8, Dims118, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+    }
+    return launch_group<256, 8, DynDims, 1>(c, ch, cfg, st, args, 1, env_smem_bytes, stream);
+}
+#endif
