@@ -432,6 +432,8 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
         if (g->line_or_sub[i] < 0 || g->line_or_sub[i] >= S || g->line_ex_sub[i] < 0 || g->line_ex_sub[i] >= S)
             return fail(nullptr, PPN_E_INVALID, "ppn_create: line end out of range");
         if (g->line_x[i] == 0.0) return fail(nullptr, PPN_E_INVALID, "ppn_create: line with zero reactance");
+        if (g->line_or_sub[i] == g->line_ex_sub[i])   // no entry in the sparse patterns (and none in the shipped grids)
+            return fail(nullptr, PPN_E_INVALID, "ppn_create: line with both ends in the same substation");
     }
     if (g->slack_sub < 0 || g->slack_sub >= S) return fail(nullptr, PPN_E_INVALID, "ppn_create: slack_sub out of range");
     if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, PPN_E_CUDA, "ppn_create: cudaSetDevice failed (no such CUDA device)");

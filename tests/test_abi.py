@@ -54,6 +54,28 @@ def test_create_rejects_bad_input_without_gpu(lib):
     assert b'null' in lib.ppn_last_error(None)
 
 
+def test_create_validates_the_grid_before_touching_the_gpu(lib):
+    """Malformed grids are refused with a message (environment.py raises ValueError on malformed input, never inside a
+    step): checked before the first CUDA call, so it runs without a GPU."""
+    import copy
+    import ctypes as C
+    import numpy as np
+    from golden_util import Fixture
+    from pypownet_b200 import _lib
+    fx = Fixture('d14_tests_basic')
+    cf = _lib.config_struct(fx.config, 'soft', False, 'natural', float(fx.case.n_sub), 0, 0)
+    out = C.c_void_p()
+    for attr, index, value, needle in (('line_ex_sub', 3, None, b'same substation'), ('line_x', 5, 0.0, b'zero reactance'),
+                                       ('line_or_sub', 0, 99, b'out of range')):
+        case = copy.copy(fx.case)
+        a = np.array(getattr(case, attr)).copy()
+        a[index] = np.array(case.line_or_sub)[index] if value is None else value
+        setattr(case, attr, a)
+        cs, keep = _lib.case_struct(case, fx.thermal_limits)
+        assert lib.ppn_create(C.byref(cs), C.byref(cf), 4, 0, C.byref(out)) == -1
+        assert needle in lib.ppn_last_error(None), lib.ppn_last_error(None)
+
+
 def test_product_package_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, 'pypownet_b200')
     for dirpath, _, files in os.walk(pkg):
