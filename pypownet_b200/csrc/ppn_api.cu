@@ -592,6 +592,7 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     //   3 hybrid sparse / dense top block  CTA per env (IEEE-118): 4.7x the dense 117^3 inverse, two CTAs per SM
     //   (2 = sparse LDL^T with level-scheduled triangular solves: correct but latency-bound, kept for reference)
     env->sparse = tpe >= 128 ? 3 : (tpe == 32 && S > 16 ? 1 : 0);
+    if (env->sparse == 3 && (env->dc.sp[0].nt > 40 || env->dc.sp[1].nt > 40)) env->sparse = 1;   // hyb_invert2 tiles hold <= 40 rows
     if (const char* v = getenv("PPN_SPARSE")) env->sparse = atoi(v);
     env->ws_dense = 2LL * NB * (NB | 1);
     const int worst = (int)env->ws_dense + env->sp_need[1] + env->sp_blob_dbl[1];

@@ -48,3 +48,27 @@ def test_ieee118_structure_is_the_documented_one(lib):
     assert lib.ppn_sparse_selfcheck(118, case.n_line, lor.ctypes.data_as(C.c_void_p), lex.ctypes.data_as(C.c_void_p), 0, 1,
                                     C.byref(err), info.ctypes.data_as(C.c_void_p)) == 0
     assert info.tolist()[:3] == [118, 265, 16]
+
+
+def test_tables_of_random_grids(lib):
+    """Any grid, not only the IEEE families: random connected line graphs (a spanning tree plus extra and parallel
+    lines), 5 to 120 substations, both structures."""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        S = int(rng.integers(5, 121))
+        lor = [int(rng.integers(0, k)) for k in range(1, S)]          # spanning tree: k attaches to an earlier node
+        lex = list(range(1, S))
+        for _ in range(int(rng.integers(0, S))):                      # extra lines, some parallel to existing ones
+            a, b = rng.integers(0, S, size=2)
+            if a != b:
+                lor.append(int(a)); lex.append(int(b))
+        lor = np.ascontiguousarray(lor, dtype=np.int32)
+        lex = np.ascontiguousarray(lex, dtype=np.int32)
+        info = np.zeros(5, dtype=np.int32)
+        for full in (0, 1):
+            err = C.c_double(-1.0)
+            rc = lib.ppn_sparse_selfcheck(S, len(lor), lor.ctypes.data_as(C.c_void_p), lex.ctypes.data_as(C.c_void_p),
+                                          full, trial, C.byref(err), info.ctypes.data_as(C.c_void_p))
+            assert rc == 0, (trial, S, lib.ppn_last_error(None))
+            assert err.value < 1e-8, (trial, S, full, err.value, info.tolist())
+            assert 0 < info[4] <= 40 or info[2] == 1, info.tolist()
