@@ -38,12 +38,16 @@ def algorithmic_bytes(case, with_obs=True):
     return chronic_in + planned_in + action_in + 2 * state + (dyn_obs if with_obs else 0) + 48
 
 
-def build_workload(grid, seed=0):
+def build_workload(grid, seed=0, cascade=False):
+    """Grid, configuration, synthetic chronics and thermal limits of a bench workload.  cascade=True swaps the shipped
+    limits (never exceeded on IEEE-30 / IEEE-118) for the synthetic ones of tools/make_cascade_limits.py
+    (1.05 x p90 of each line's do-nothing flow), so that the cascading-failure loop fires."""
     from pypownet_b200.case import Case
     from pypownet_b200 import synthetic
     case = Case.builtin(grid)
     with open(os.path.join(ROOT, 'pypownet_b200', 'data', grid + '.json')) as f:
-        imaps = np.array(json.load(f)['imaps'], dtype=np.float64)
+        d = json.load(f)
+    imaps = np.array(d['imaps_cascade' if cascade and 'imaps_cascade' in d else 'imaps'], dtype=np.float64)
     chronics = synthetic.make_chronics(case, N_CHRONICS, N_ROWS, seed=seed, thermal_limits=imaps)
     return case, synthetic.default_config(grid), chronics, imaps
 
@@ -52,6 +56,22 @@ def env_starts(n_envs, offset=0):
     """env e plays chronic e mod 12 from row (e // 12) mod (T - 1) (SURVEY.md 8d config 2); e is the GLOBAL index."""
     from pypownet_b200.sharding import env_starts as starts
     return starts(N_CHRONICS, N_ROWS, offset, offset + n_envs)
+
+
+def random_action_bank(case, n_envs, n_batches=16, seed=1234):
+    """RandomNodeSplitting + RandomLineSwitch (agent.py:78-158): per env and step one substation
+    with its element bits i.i.d. Bernoulli(1/2) plus one line switch.  uint8 [n_batches, n_envs, action_length]; the
+    bench cycles through the pre-drawn batches."""
+    rng = np.random.default_rng(seed)
+    elem_sub = np.asarray(case.elem_sub)
+    nt_ = len(elem_sub)
+    bank = np.zeros((n_batches, n_envs, case.action_length), dtype=np.uint8)
+    for k in range(n_batches):
+        subs = rng.integers(0, case.n_sub, size=n_envs)
+        bits = rng.integers(0, 2, size=(n_envs, nt_), dtype=np.uint8)
+        bank[k, :, :nt_] = bits * (elem_sub[None, :] == subs[:, None])
+        bank[k, np.arange(n_envs), nt_ + rng.integers(0, case.n_line, size=n_envs)] = 1
+    return bank
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (port)
@@ -221,18 +241,7 @@ def run_b200(args):
     actions = torch.zeros((B, case.action_length), dtype=torch.uint8, device=dev)      # do-nothing agent
     action_bank = None
     if args.agent == 'random':
-        # RandomNodeSplitting + RandomLineSwitch (agent.py:78-158): per env and step one
-        # substation with its element bits i.i.d. Bernoulli(1/2) plus one line switch; 16 pre-drawn batches, cycled
-        rng = np.random.default_rng(1234 + rank)
-        elem_sub = np.asarray(case.elem_sub)
-        bank = np.zeros((16, B, case.action_length), dtype=np.uint8)
-        nt_ = len(elem_sub)
-        for k in range(16):
-            subs = rng.integers(0, case.n_sub, size=B)
-            bits = rng.integers(0, 2, size=(B, nt_), dtype=np.uint8)
-            bank[k, :, :nt_] = bits * (elem_sub[None, :] == subs[:, None])
-            bank[k, np.arange(B), nt_ + rng.integers(0, case.n_line, size=B)] = 1
-        action_bank = torch.from_numpy(bank).to(dev)
+        action_bank = torch.from_numpy(random_action_bank(case, B, seed=1234 + rank)).to(dev)
     step_counter = [0, 0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # Sharded runs: the step kernel writes the packed (reward[5], done, flag) rows itself and one NCCL all-gather per

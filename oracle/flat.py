@@ -543,6 +543,49 @@ class FlatEnv(object):
             if not self._cascade():
                 return self.observation_dynamic()
 
+    # ----------------------------------------------------------------------------- state rows (kernel layout)
+    def export_rows(self):
+        """The env state as the three rows of the CUDA library (include/pypownet_b200.h PPN_STATE_*): real
+        (Vm | Va deg | load P | load Q | gen Pg | Qg | Vg), topology (node bits | line status | gen status), counters
+        (reconnectable | line cooldown | soft-overflow count | node cooldown | cursor[4])."""
+        _, lbus, _, _ = self._buses()
+        real = np.concatenate((self.vm, self.va, self.pd[lbus], self.qd[lbus], self.gen_pg, self.gen_qg,
+                               self.gen_vg)).astype(np.float64)
+        topo = np.concatenate((self.gen_node, self.load_node, self.or_node, self.ex_node, self.status,
+                               self.gen_status)).astype(np.uint8)
+        row = -1 if self.row is None else (-2 if self.row == 'id0' else int(self.row))
+        cnt = np.concatenate((self.t_reconnectable, self.t_line_react, self.soft_count, self.t_node_react,
+                              [self.chronic_id, row, self.next_chronic, 0])).astype(np.int32)
+        return real, topo, cnt
+
+    def import_rows(self, real, topo, cnt):
+        """Inverse of export_rows (test harness: re-synchronisation of a replay after a floating-pocket step)."""
+        S, G, L, N, NB = self.S, self.G, self.L, self.N, 2 * self.S
+        real, topo, cnt = np.asarray(real, dtype=np.float64), np.asarray(topo), np.asarray(cnt)
+        self.vm, self.va = real[:NB].copy(), real[NB:2 * NB].copy()
+        o = 2 * NB
+        self.gen_node = topo[:G].astype(np.int64)
+        self.load_node = topo[G:G + L].astype(np.int64)
+        self.or_node = topo[G + L:G + L + N].astype(np.int64)
+        self.ex_node = topo[G + L + N:G + L + 2 * N].astype(np.int64)
+        self.status = topo[G + L + 2 * N:G + L + 3 * N].astype(np.int64)
+        self.gen_status = topo[G + L + 3 * N:2 * G + L + 3 * N].astype(np.int64)
+        lbus = self.c.load_sub + S * self.load_node
+        self.pd, self.qd = np.zeros(NB), np.zeros(NB)
+        self.pd[lbus], self.qd[lbus] = real[o:o + L], real[o + L:o + 2 * L]
+        o += 2 * L
+        self.gen_pg, self.gen_qg, self.gen_vg = real[o:o + G].copy(), real[o + G:o + 2 * G].copy(), \
+            real[o + 2 * G:o + 3 * G].copy()
+        self.t_reconnectable = cnt[:N].astype(np.float64)
+        self.t_line_react = cnt[N:2 * N].astype(np.float64)
+        self.soft_count = cnt[2 * N:3 * N].astype(np.float64)
+        self.t_node_react = cnt[3 * N:3 * N + S].astype(np.float64)
+        cur = cnt[3 * N + S:3 * N + S + 4]
+        self.chronic_id, self.next_chronic = int(cur[0]), int(cur[2])
+        self.row = None if cur[1] == -1 else ('id0' if cur[1] == -2 else int(cur[1]))
+        self.entries_row, self.entries_chronic = (self.row if isinstance(self.row, int) else None), self.chronic_id
+        self.flows = np.zeros((N, 4))
+
     def _apply_action_nodes_to_initial(self):
         S = self.S
         for lo in np.flatnonzero(self.load_node != 0):

@@ -37,10 +37,21 @@ class Fixture(object):
                                                       self.thermal_limits))
         for k in ('obs0', 'actions', 'obs', 'reward', 'done', 'flag', 'reset_obs'):
             setattr(self, k, z[k])
+        # steps where the unmodified reference and the oracle disagree on done/flag (floating pockets: the reference's
+        # outcome there is SuperLU rounding noise).  The reference's state after such a step is
+        # recorded as state rows (resync_*) and every replay continues from it.
+        n = len(self.actions)
+        self.mismatch = z['mismatch'] if 'mismatch' in z.files else np.zeros(n, dtype=bool)
+        self.resync = {}
+        for k, t in enumerate(np.flatnonzero(self.mismatch)):
+            self.resync[int(t)] = (z['resync_real'][k], z['resync_topo'][k], z['resync_cnt'][k])
+        self.obs_width = self.obs.shape[1] if n else self.case.obs_length     # compact fixtures: dynamic prefix only
         self.has_sim = 'sim_actions' in z.files
         if self.has_sim:
             for k in ('sim_actions', 'sim_obs', 'sim_reward', 'sim_done', 'sim_flag'):
                 setattr(self, k, z[k])
+            self.sim_mismatch = z['sim_mismatch'] if 'sim_mismatch' in z.files else \
+                np.zeros(len(self.sim_actions), dtype=bool)
 
 
 def _chronic_from_arrays(name, tabs, ids, datetimes, imaps):

@@ -19,17 +19,31 @@ def vec_env(fx, B, **kw):
                      reward_constant=fx.reward_constant, thermal_limits=fx.thermal_limits, **kw)
 
 
+def set_rows(env, rows, B):
+    from pypownet_b200 import _lib
+    for field, row in zip((_lib.STATE_REAL, _lib.STATE_TOPOLOGY, _lib.STATE_COUNTERS), rows):
+        env.set_state(field, torch.from_numpy(np.repeat(np.asarray(row)[None], B, axis=0)))
+
+
 @pytest.mark.parametrize('name', fixture_names())
 def test_cuda_reproduces_reference_fixture(name):
     fx = Fixture(name)
     B = 3
     env = vec_env(fx, B)
     nd = fx.case.obs_dynamic_length
+    W = fx.obs_width
     obs0 = env.obs.cpu().numpy()
     assert np.max(np.abs(obs0[0] - fx.obs0)) < TOL
     worst = 0.0
     for t in range(len(fx.actions)):
-        if fx.has_sim:
+        if fx.mismatch[t]:
+            # floating pocket: the reference's outcome is decided by the rounding of a singular
+            # SuperLU pivot; the library reports "diverging", and the replay continues from the reference's state
+            obs, reward, done, flag = env.step(np.repeat(fx.actions[t][None], B, axis=0))
+            assert np.all(done.cpu().numpy() == 1) and np.all(flag.cpu().numpy() == 2), t
+            set_rows(env, fx.resync[t], B)
+            continue
+        if fx.has_sim and not fx.sim_mismatch[t]:
             so, sr, sd, sf = env.simulate(np.repeat(fx.sim_actions[t][None], B, axis=0))
             assert bool(sd[1].item()) == bool(fx.sim_done[t]) and int(sf[1].item()) == int(fx.sim_flag[t]), t
             if not fx.sim_done[t]:
@@ -48,10 +62,12 @@ def test_cuda_reproduces_reference_fixture(name):
             expect = fx.obs[t]
         got = obs.cpu().numpy()
         assert np.array_equal(got[0], got[B - 1])
-        err = float(np.max(np.abs(got[0] - expect)))
-        assert err < TOL, 'step %d: |cuda - reference| = %g at %d' % (t, err, int(np.argmax(np.abs(got[0] - expect))))
+        err = float(np.max(np.abs(got[0, :W] - expect)))
+        assert err < TOL, 'step %d: |cuda - reference| = %g at %d' % (t, err, int(np.argmax(np.abs(got[0, :W] - expect))))
         worst = max(worst, err)
     assert worst < TOL
+    print('%s: %d steps replayed, %d floating-pocket mismatches, max |cuda - reference| = %.3g'
+          % (name, len(fx.actions), int(fx.mismatch.sum()), worst))
 
 
 @pytest.mark.parametrize('name,steps', [('d14_ac_random', 120), ('d30_ac_random', 60), ('d118_ac_random', 25),

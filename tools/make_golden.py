@@ -7,8 +7,12 @@ to the GPU box, the fixtures do.
 Each fixture is self-contained: truncated chronic tables (float32, as parsed by the reference), configuration,
 thermal limits, the action stream, and per step the reference's outputs through RunEnv.step / simulate /
 process_game_over (environment.py:848-888): full observation vector, five sub-rewards, done, flag code.
-oracle/flat.py is run in lockstep; the fixture stops at the first step where the two disagree on a discrete outcome
-(only happens on grids with a floating pocket, see oracle/flat.py header) and records why in `note`.
+oracle/flat.py is run in lockstep.  The FULL reference run is recorded: a step where reference and oracle disagree
+on a discrete outcome (only grids with a floating pocket, whose outcome in the reference is SuperLU rounding noise --
+oracle/flat.py header) is kept with `mismatch[t] = True`, and the state of the reference after
+that step (after its process_game_over when it ended the game) is stored as state rows of the CUDA library
+(`resync_*`), from which the oracle here and every replay in tests/ continue.  Nothing is truncated; tests report
+the mismatch count.
 """
 import json
 import os
@@ -43,7 +47,11 @@ SCENARIOS = {
     'd30_ac_random': (P + '/default30', 'case30', 'ab', 100, 120, 'random', 'soft', {}, True, 5),
     'd118_ac_nothing': (P + '/default118', 'case118', 'ab', 40, 50, 'nothing', 'soft', {}, False, 0),
     'd118_ac_random': (P + '/default118', 'case118', 'ab', 40, 50, 'random', 'soft', {}, False, 6),
+    # BASELINE.json configs[0]: default14 DC, do-nothing agent, 1000 timesteps, single env (chronic a rolls into b)
+    'd14_dc_nothing_1000': (P + '/default14', 'case14', 'ab', None, 1000, 'nothing', 'soft', {'loadflow_mode': 'DC'},
+                            False, 0),
 }
+COMPACT = ('d14_dc_nothing_1000',)       # observations stored as their dynamic prefix only (static tail = obs0's)
 
 
 def build_folder(src, chronics, rows, overrides, dst):
@@ -106,6 +114,34 @@ def make_action(rng, case, agent):
     return a
 
 
+def reference_rows(game, case, chron):
+    """State of the reference's Game (game.py:306-334, grid.py mpc tables) as the three state rows of the CUDA
+    library (oracle.flat.FlatEnv.export_rows layout)."""
+    grid = game.grid
+    mpc = grid.mpc
+    bus, gen, br = mpc['bus'], mpc['gen'], mpc['branch']
+    S = case.n_sub
+    real_ids = case.sub_ids.astype(np.int64)
+    gnode = (gen[:, 0].astype(np.int64) != real_ids[case.gen_sub]).astype(np.uint8)
+    onode = (br[:, 0].astype(np.int64) != real_ids[case.line_or_sub]).astype(np.uint8)
+    enode = (br[:, 1].astype(np.int64) != real_ids[case.line_ex_sub]).astype(np.uint8)
+    are_loads = np.asarray(grid.are_loads, dtype=bool)
+    lnode = are_loads[case.load_sub + S].astype(np.uint8)
+    assert np.all(are_loads[case.load_sub + S * lnode]) and are_loads.sum() == case.n_load
+    lbus = case.load_sub + S * lnode
+    real = np.concatenate((bus[:, 7], bus[:, 8], bus[lbus, 2], bus[lbus, 3], gen[:, 1], gen[:, 2], gen[:, 5]))
+    topo = np.concatenate((gnode, lnode, onode, enode, (br[:, 10] != 0).astype(np.uint8),
+                           (gen[:, 7] > 0).astype(np.uint8)))
+    ch = game._Game__chronic
+    names = [c.name for c in chron.chronics]
+    ids = list(ch.get_timestep_ids())
+    cnt = np.concatenate((game.timesteps_before_lines_reconnectable, game.timesteps_before_lines_reactionable,
+                          game.n_timesteps_soft_overflowed_lines, game.timesteps_before_nodes_reactionable,
+                          [names.index(ch.name), ids.index(game.current_timestep_id),
+                           game._Game__chronic_looper.next_chronic_id, 0]))
+    return real.astype(np.float64), topo.astype(np.uint8), cnt.astype(np.int32)
+
+
 def run(name):
     import logging
     logging.disable(logging.CRITICAL)
@@ -129,51 +165,66 @@ def run(name):
     rng = np.random.default_rng(seed)
     OBS = case.obs_length
     rec = {k: [] for k in ('actions', 'obs', 'reward', 'done', 'flag', 'reset_obs', 'sim_actions', 'sim_obs',
-                           'sim_reward', 'sim_done', 'sim_flag')}
+                           'sim_reward', 'sim_done', 'sim_flag', 'mismatch', 'sim_mismatch', 'resync_real',
+                           'resync_topo', 'resync_cnt')}
     obs0 = env._get_obs().as_array()
-    note = ''
+    notes = []
+    compact = name in COMPACT
+    nd = case.obs_dynamic_length
+    keep = (lambda o: o[:nd]) if compact else (lambda o: o)
+    OW = nd if compact else OBS
     worst = float(np.max(np.abs(obs0 - fe.observation())))
     for it in range(n_steps):
         if do_sim:
             sa = make_action(rng, case, 'random')
             so, sr, sd, sf = env.simulate(sa.astype(np.int64), do_sum=False)
             so2, sr2, sd2, sf2, _ = fe.simulate(sa)
-            if sd != sd2 or flag_code(sf) != sf2:
-                note = 'stopped before step %d: simulate disagreement (reference done=%s flag=%d, oracle done=%s ' \
-                       'flag=%d)' % (it, sd, flag_code(sf), sd2, sf2)
-                break
+            sim_bad = sd != sd2 or flag_code(sf) != sf2
+            if sim_bad:
+                notes.append('simulate %d: reference done=%s flag=%d, oracle done=%s flag=%d' % (
+                    it, sd, flag_code(sf), sd2, sf2))
+            rec['sim_mismatch'].append(bool(sim_bad))
             rec['sim_actions'].append(sa)
-            rec['sim_obs'].append(np.full(OBS, np.nan) if so is None else so)
+            rec['sim_obs'].append(np.full(OW, np.nan) if so is None else keep(so))
             rec['sim_reward'].append(np.asarray(sr, dtype=np.float64) if len(sr) == 5 else np.full(5, np.nan))
             rec['sim_done'].append(bool(sd))
             rec['sim_flag'].append(flag_code(sf))
-            if so is not None:
+            if so is not None and not sim_bad:
                 worst = max(worst, float(np.max(np.abs(so[:len(so2)] - so2))))
         a = make_action(rng, case, agent)
         o, r, d, f = env.step(a.astype(np.int64), do_sum=False)
         o2, r2, d2, f2, _ = fe.step(a)
-        if d != d2 or flag_code(f) != f2:
-            note = 'stopped before step %d: reference done=%s flag=%d (%s), oracle done=%s flag=%d' % (
-                it, d, flag_code(f), getattr(f, 'text', ''), d2, f2)
-            break
+        bad = d != d2 or flag_code(f) != f2
+        if bad:
+            notes.append('step %d: reference done=%s flag=%d (%s), oracle done=%s flag=%d' % (
+                it, d, flag_code(f), getattr(f, 'text', ''), d2, f2))
+        rec['mismatch'].append(bool(bad))
         rec['actions'].append(a)
-        rec['obs'].append(np.full(OBS, np.nan) if o is None else o)
+        rec['obs'].append(np.full(OW, np.nan) if o is None else keep(o))
         rec['reward'].append(np.asarray(r, dtype=np.float64) if len(r) == 5 else np.full(5, np.nan))
         rec['done'].append(bool(d))
         rec['flag'].append(flag_code(f))
-        if o is not None:
+        if o is not None and not bad:
             worst = max(worst, float(np.max(np.abs(o[:len(o2)] - o2))))
         if d:
             ro = env.process_game_over()
+            rec['reset_obs'].append(keep(ro))
+        else:
+            rec['reset_obs'].append(np.full(OW, np.nan))
+        if bad:
+            # the replay continues from the reference's state (after its process_game_over, if it ended the game)
+            rows = reference_rows(env.game, case, chron)
+            fe.import_rows(*rows)
+            for k, v in zip(('resync_real', 'resync_topo', 'resync_cnt'), rows):
+                rec[k].append(v)
+        elif d:
             ro2 = fe.process_game_over()
             worst = max(worst, float(np.max(np.abs(ro[:len(ro2)] - ro2))))
-            rec['reset_obs'].append(ro)
-        else:
-            rec['reset_obs'].append(np.full(OBS, np.nan))
     n = len(rec['actions'])
+    note = '; '.join(notes)
     out = {'casename': casename, 'config': json.dumps(cfgd), 'mode': mode, 'default_reward': default_reward,
            'reward_constant': cfg.reward_constant, 'thermal_limits': np.asarray(chron[0].imaps, dtype=np.float64),
-           'obs0': obs0, 'note': note, 'n_chronics': len(chron)}
+           'obs0': obs0, 'note': note, 'n_chronics': len(chron), 'compact': compact}
     for i, ch in enumerate(chron.chronics):
         for t in TABLES:
             out['chronic%d_%s' % (i, t)] = getattr(ch, t)
@@ -182,25 +233,33 @@ def run(name):
         out['chronic%d_name' % i] = ch.name
     A = case.action_length
     out['actions'] = np.array(rec['actions'], dtype=np.uint8).reshape(n, A)
-    out['obs'] = np.array(rec['obs'], dtype=np.float64).reshape(n, OBS)
+    out['obs'] = np.array(rec['obs'], dtype=np.float64).reshape(n, OW)
     out['reward'] = np.array(rec['reward'], dtype=np.float64).reshape(n, 5)
     out['done'] = np.array(rec['done'], dtype=bool)
     out['flag'] = np.array(rec['flag'], dtype=np.int32)
-    out['reset_obs'] = np.array(rec['reset_obs'], dtype=np.float64).reshape(n, OBS)
+    out['reset_obs'] = np.array(rec['reset_obs'], dtype=np.float64).reshape(n, OW)
+    out['mismatch'] = np.array(rec['mismatch'], dtype=bool)
+    nm = int(out['mismatch'].sum())
+    S_, G_, L_, N_ = case.n_sub, case.n_gen, case.n_load, case.n_line
+    out['resync_real'] = np.array(rec['resync_real'], dtype=np.float64).reshape(nm, 4 * S_ + 2 * L_ + 3 * G_)
+    out['resync_topo'] = np.array(rec['resync_topo'], dtype=np.uint8).reshape(nm, 2 * G_ + L_ + 3 * N_)
+    out['resync_cnt'] = np.array(rec['resync_cnt'], dtype=np.int32).reshape(nm, 3 * N_ + S_ + 4)
     if do_sim:
         m = len(rec['sim_actions'])
         out['sim_actions'] = np.array(rec['sim_actions'], dtype=np.uint8).reshape(m, A)
-        out['sim_obs'] = np.array(rec['sim_obs'], dtype=np.float64).reshape(m, OBS)
+        out['sim_obs'] = np.array(rec['sim_obs'], dtype=np.float64).reshape(m, OW)
         out['sim_reward'] = np.array(rec['sim_reward'], dtype=np.float64).reshape(m, 5)
         out['sim_done'] = np.array(rec['sim_done'], dtype=bool)
         out['sim_flag'] = np.array(rec['sim_flag'], dtype=np.int32)
+        out['sim_mismatch'] = np.array(rec['sim_mismatch'], dtype=bool)
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + '.npz')
     np.savez_compressed(path, **out)
     flags = np.bincount(out['flag'], minlength=5).tolist()
-    line = '%-26s steps=%3d/%3d game-overs=%3d flags[none,illegal,diverging,loads,prods]=%s ' \
-           'max|reference-oracle|=%.2e size=%dKB %s' % (name, n, n_steps, int(out['done'].sum()), flags, worst,
-                                                        os.path.getsize(path) // 1024, note)
+    line = '%-26s steps=%4d/%4d game-overs=%3d flags[none,illegal,diverging,loads,prods]=%s ' \
+           'max|reference-oracle|=%.2e pocket-mismatches=%d (+%d simulate) size=%dKB %s' % (
+               name, n, n_steps, int(out['done'].sum()), flags, worst, nm,
+               int(out['sim_mismatch'].sum()) if do_sim else 0, os.path.getsize(path) // 1024, note)
     print(line)
     return line
 
