@@ -188,24 +188,32 @@ def run_reference(args):
         busy += b
     pool.close()
     value = total / busy
-    sample = '%d processes x %d do-nothing env-steps of %s per bench step, synthetic chronics' % (cores, per_step,
-                                                                                                  args.grid)
+    sample = '%d processes (one env each) x %d do-nothing env-steps of %s per bench step, synthetic chronics' % (
+        cores, per_step, args.grid)
+    cfg = workload_config(args, None)
+    cfg['workload'] = 'CPU arm: %s AC, do-nothing agent, restart on game over; BOUNDED SAMPLE of the 4096-env workload: ' \
+                      '%d single-env processes x %d env-steps per bench step (oracle/flat.py on the host cores)' % (
+                          GRIDS[args.grid], cores, per_step)
     line = {'impl': 'reference', 'metric': 'env steps/sec (batched grids)', 'value': value, 'unit': 'env-steps/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * busy / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args, None),
+            'config': cfg,
             'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
 
 
+def workload_name(grid, envs, agent, cascade):
+    return '%s AC%s, %d batched envs per GPU, %s agent, auto-restart on game over' % (
+        GRIDS[grid], ' with synthetic thermal limits (cascading-failure loop fires)' if cascade else '', envs,
+        'do-nothing' if agent == 'nothing' else 'random node-split + line-switch')
+
+
 def workload_config(args, extra):
-    cfg = {'workload': '%s AC, %d batched envs per GPU, %s agent, auto-restart on game over '
-                       '(BASELINE.json configs[1] shape)' % (GRIDS[args.grid], args.envs,
-                                                            'do-nothing' if args.agent == 'nothing' else
-                                                            'random node-split + line-switch'),
+    cfg = {'workload': workload_name(args.grid, args.envs, args.agent, args.cascade) +
+           ' (BASELINE.json configs[1] shape)',
            'grid': args.grid, 'envs_per_gpu': args.envs, 'chronics': '%d synthetic x %d rows' % (N_CHRONICS, N_ROWS),
            'solver': 'fast-decoupled XB, tol 1e-6, <=25 it (the reference\'s PF_ALG=2)',
            'l2': 'flushed between timed steps (256 MiB write)', 'parallelism': 'env-sharded, dp%d' % args.gpus}
@@ -214,170 +222,261 @@ def workload_config(args, extra):
     return cfg
 
 
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    import __graft_entry__ as graft
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    torch.cuda.set_device(local)
-    if rank == 0:
-        graft.build()
-    if world > 1:
-        dist.barrier()
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def traffic_of(grid, envs, agent):
+    """DRAM bytes per launch of the step kernel from the committed ncu captures (profiles/traffic.json), or None."""
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(tpath):
+        return None
+    with open(tpath) as f:
+        t = json.load(f)
+    return t.get('%s_%d%s' % (grid, envs, '' if agent == 'nothing' else '_' + agent))
+
+
+class Ctx(object):
+    """torch / torch.distributed handles of this process."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if self.world > 1:
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_list(self, values):
+        """[world][len(values)] float64 on every rank."""
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world == 1:
+            return [t.cpu().tolist()]
+        out = self.torch.zeros((self.world, len(values)), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_gather_into_tensor(out, t)
+        return out.cpu().tolist()
+
+
+def measure(ctx, grid, envs, agent, cascade, steps, warmup, with_e2e=True, sampler=None, profile=False):
+    """One workload on this process' GPU (and, under torchrun, on every rank at once: weak scaling).  Returns a dict."""
+    torch = ctx.torch
     from pypownet_b200.vec_env import VecRunEnv
     from pypownet_b200 import sharding
-    dev = torch.device('cuda', local)
-    case, cfg, chronics, imaps = build_workload(args.grid)
-    B = args.envs
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    case, cfg, chronics, imaps = build_workload(grid, cascade=cascade)
+    B = envs
     # weak scaling: the global batch of world * B envs is dealt round-robin, rank r owns envs r, r + world, ...
     sc, sr = sharding.env_starts_of(N_CHRONICS, N_ROWS, sharding.strided_env_ids(B, rank, world))
-    env = VecRunEnv(case, cfg, chronics, B, device=local, reward_constant=float(case.n_sub), thermal_limits=imaps,
+    env = VecRunEnv(case, cfg, chronics, B, device=ctx.local, reward_constant=float(case.n_sub), thermal_limits=imaps,
                     start_chronics=sc, start_rows=sr)
     actions = torch.zeros((B, case.action_length), dtype=torch.uint8, device=dev)      # do-nothing agent
     action_bank = None
-    if args.agent == 'random':
+    if agent == 'random':
         action_bank = torch.from_numpy(random_action_bank(case, B, seed=1234 + rank)).to(dev)
-    step_counter = [0, 0]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    # Sharded runs: the step kernel writes the packed (reward[5], done, flag) rows itself and one NCCL all-gather per
-    # step brings every shard's rows to every rank.  The gather of step t runs on NCCL's stream while step t+1 is
-    # already computing (two pack / result buffers); it is waited for inside the timed interval of step t+1, the last
-    # one before the closing synchronisation, so every collective completes inside the timed region.
-    packs = [torch.zeros((B, sharding.PACK_WIDTH), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
-    gathered = [torch.zeros((world * B, sharding.PACK_WIDTH), dtype=torch.float64, device=dev) for _ in range(2)] \
-        if world > 1 else None
-    works = [None, None]
+    # Sharded runs: every rank's step kernel stores its packed (reward[5], done, flag) rows straight into rank 0's
+    # GPU memory over NVLink (sharding.PeerGather); rank 0 copies the rows of step t-1 to the host on a side stream
+    # while step t computes.  No collective between two steps: ranks never run in lock-step.
+    pg = sharding.PeerGather(env, rank, world) if world > 1 else None
+    tstep = [0]
 
     def one_step():
-        a = actions
-        if action_bank is not None:
-            a = action_bank[step_counter[0] % 16]
-            step_counter[0] += 1
-        if world > 1:
-            buf = step_counter[1] & 1
-            step_counter[1] += 1
-            env.enable_result_pack(packs[buf])
+        t = tstep[0]
+        tstep[0] += 1
+        a = actions if action_bank is None else action_bank[t % 16]
+        if pg is not None:
+            pg.before_step(t)
         obs, reward, done, flag = env.step(a, auto_reset=True)
-        if world > 1:      # rewards / dones / flags of every shard on every rank (NCCL over NVLink)
-            if works[buf ^ 1] is not None:
-                works[buf ^ 1].wait()          # the previous step's gather (stream wait, not a host block)
-            works[buf] = dist.all_gather_into_tensor(gathered[buf], packs[buf], async_op=True)
+        if pg is not None:
+            pg.after_step(t)
+            if t >= 1:
+                pg.collect(t - 1)
         return done
 
     def drain():
-        for w in works:
-            if w is not None:
-                w.wait()
+        """the rows of the last step reach the host inside the timed region too"""
+        if pg is not None and pg.is_root:
+            pg.collect(tstep[0] - 1)
+            torch.cuda.current_stream().wait_stream(pg.side)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(warmup, 3)
+    for _ in range(warm):
         one_step()
-        flush.fill_(1)
+        ctx.flush.fill_(1)
+    if pg is not None and pg.is_root:
+        pg.collect(tstep[0] - 1)
+        pg.wait_all()
     torch.cuda.synchronize()
     c0 = env.counters()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
+    ctx.barrier()
     if sampler:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     n_done = torch.zeros((), dtype=torch.int64, device=dev)
     wall0 = time.perf_counter()
-    for k in range(args.steps):
+    if pg is not None:
+        # the root's collect() calls of the timed loop start at the first timed step
+        pass
+    for k in range(steps):
         ev[k][0].record()
         d = one_step()
-        if k == args.steps - 1:
-            drain()                                      # the last gather also completes inside the timed region
+        if k == steps - 1:
+            drain()
         ev[k][1].record()
         n_done += d.sum()
-        flush.fill_(k & 1)                               # evict state/observation/chronics from L2 (126 MB)
+        ctx.flush.fill_(k & 1)                           # evict state/observation/chronics from L2 (126 MB)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    my_wall = time.perf_counter() - wall0
+    ctx.barrier()
     wall = time.perf_counter() - wall0
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    ms = sum(per_step)
+    ms_max = ctx.max_over_ranks(ms)
     c1 = env.counters()
     launches = c1['kernel_launches'] - c0['kernel_launches']
-    value = world * B * args.steps / (ms_max * 1e-3)
+    value = world * B * steps / (ms_max * 1e-3)
+    per_rank = ctx.gather_list([ms / steps, max(per_step), my_wall * 1e3 / steps])
 
     # ---- warm-L2 back-to-back figure (the natural RL loop: state stays in L2 between steps)
-    torch.cuda.synchronize()
+    ctx.barrier()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         one_step()
     drain()
     a1.record()
     torch.cuda.synchronize()
-    warm_value = world * B * args.steps / (a0.elapsed_time(a1) * 1e-3)
+    warm_value = world * B * steps / (ctx.max_over_ranks(a0.elapsed_time(a1)) * 1e-3)
+    if pg is not None:
+        pg.wait_all()
+
+    out = {'grid': grid, 'envs_per_gpu': B, 'agent': agent, 'cascade': cascade, 'value': value,
+           'ms_per_step': ms_max / steps, 'warm_l2_value': warm_value, 'launches': launches, 'wall': wall,
+           'per_rank_ms_per_step': [round(r[0], 4) for r in per_rank],
+           'per_rank_slowest_step_ms': [round(r[1], 4) for r in per_rank],
+           'per_rank_host_ms_per_step': [round(r[2], 4) for r in per_rank]}
+    steps_done = c1['env_steps'] - c0['env_steps']
+    out['counters'] = {
+        'loadflows_per_env_step': (c1['loadflows'] - c0['loadflows']) / max(steps_done, 1),
+        'fd_iterations_per_loadflow': (c1['fd_iterations'] - c0['fd_iterations']) / max(c1['loadflows'] - c0['loadflows'], 1),
+        'game_over_rate': float(n_done.item()) / (B * steps),
+        'max_cascade_depth': c1['max_cascade_depth'],
+        'cascade_depth_histogram': c1['cascade_depth_histogram'],
+        'threads_per_env': c1['threads_per_env'], 'smem_bytes_per_env': c1['smem_bytes_per_env']}
+    A = algorithmic_bytes(case)
+    peak, peak_src = hbm_peak()
+    kernel_ms = ms_max / steps
+    achieved = A * B / (kernel_ms * 1e-3) / 1e9
+    out['algorithmic_bytes_per_env_step'] = A
+    out['roofline'] = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                       'traffic': traffic_of(grid, B, agent), 'peak_source': peak_src,
+                       'kernel': 'ppn_step_kernel (step + restart launches of one env-step)', 'kernel_ms': kernel_ms}
 
     # ---- end to end through the public API with host buffers (pinned), copies inside the timed region
-    act_pinned = torch.zeros((B, case.action_length), dtype=torch.uint8).pin_memory()
-    host_bank = [action_bank[k].cpu().pin_memory() for k in range(16)] if action_bank is not None else None
-    for _ in range(3):
-        env.step_pinned(act_pinned)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        po, pr, pd, pf = env.step_pinned(host_bank[k % 16] if host_bank is not None else act_pinned)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(t.item())
-    clocks = sampler.stop() if sampler else None      # sampled over the timed, back-to-back and end-to-end loops
-    h2d = B * case.action_length
-    d2h = B * (case.obs_dynamic_length * 8 + 5 * 8 + 1 + 4)
+    if with_e2e:
+        act_pinned = torch.zeros((B, case.action_length), dtype=torch.uint8).pin_memory()
+        host_bank = [action_bank[k].cpu().pin_memory() for k in range(16)] if action_bank is not None else None
+        for _ in range(3):
+            env.step_pinned(act_pinned)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            po, pr, pd, pf = env.step_pinned(host_bank[k % 16] if host_bank is not None else act_pinned)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_all = ctx.gather_list([e2e_s])
+        e2e_value = world * B * steps / max(r[0] for r in e2e_all)
+        h2d = B * case.action_length
+        d2h = B * (case.obs_dynamic_length * 8 + 5 * 8 + 1 + 4)
+        out['e2e'] = {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h}
+        out['per_rank_e2e_ms_per_step'] = [round(1e3 * r[0] / steps, 4) for r in e2e_all]
+        out['per_rank_e2e_d2h_gbs'] = [round(d2h * steps / r[0] / 1e9, 2) for r in e2e_all]
+    if pg is not None:
+        pg.close()
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+    return out
 
+
+def run_b200(args):
+    import __graft_entry__ as graft
+    ctx = Ctx()
+    if ctx.rank == 0:
+        graft.build()
+    ctx.barrier()
+    world, rank = ctx.world, ctx.rank
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
+    m = measure(ctx, args.grid, args.envs, args.agent, args.cascade, args.steps, args.warmup, sampler=sampler)
+    # ---- the other BASELINE configurations, measured in the same run (fewer steps): configs[2] IEEE-30 with the
+    # cascading-failure loop firing, configs[3] IEEE-118 do-nothing, configs[4] IEEE-118 with the random agent.  Under
+    # `--gpus 8` configs[3] is 65536 envs and configs[4] 32768 envs over the 8 GPUs.
+    secondary = []
+    if not args.no_secondary:
+        k = max(10, min(args.steps // 4, 40))
+        for name, grid, envs, agent, cascade in (
+                ('configs[2] default30 AC + cascade, 8192 envs per GPU', 'case30', 8192, 'nothing', True),
+                ('configs[3] default118 AC, 8192 envs per GPU (65536 over 8 GPUs)', 'case118', 8192, 'nothing', False),
+                ('configs[4] default118 AC, random node-split + line-switch, 4096 envs per GPU (32768 over 8 GPUs)',
+                 'case118', 4096, 'random', False)):
+            r = measure(ctx, grid, envs, agent, cascade, k, 3, with_e2e=True)
+            secondary.append({'workload': name, 'grid': grid, 'envs_per_gpu': envs, 'n_gpus': world, 'steps': k,
+                              'value': r['value'], 'unit': 'env-steps/s', 'ms_per_step': r['ms_per_step'],
+                              'e2e': r['e2e']['value'], 'roofline_frac': r['roofline']['frac'],
+                              'algorithmic_bytes_per_env_step': r['algorithmic_bytes_per_env_step'],
+                              'gpu_launches': r['launches'], 'per_rank_ms_per_step': r['per_rank_ms_per_step'],
+                              'counters': r['counters']})
+    clocks = sampler.stop() if sampler else None          # sampled over every timed loop of this run
+    if args.profile_ranks and rank == 0:
+        with open(args.profile_ranks, 'a') as f:
+            f.write('# n_gpus=%d grid=%s envs_per_gpu=%d agent=%s: per rank  kernel ms/step | slowest step ms | host ms/step'
+                    ' | e2e ms/step | e2e D2H GB/s\n' % (world, args.grid, args.envs, args.agent))
+            for r in range(world):
+                f.write('rank %d  %.4f  %.4f  %.4f  %.4f  %.2f\n' % (
+                    r, m['per_rank_ms_per_step'][r], m['per_rank_slowest_step_ms'][r], m['per_rank_host_ms_per_step'][r],
+                    m['per_rank_e2e_ms_per_step'][r], m['per_rank_e2e_d2h_gbs'][r]))
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            ctx.dist.destroy_process_group()
         return
-    A = algorithmic_bytes(case)
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(peaks_path):
-        with open(peaks_path) as f:
-            peak, peak_src = float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
-    else:
-        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    kernel_ms = ms_max / args.steps
-    achieved = A * B / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get('%s_%d' % (args.grid, B))
-    steps_done = c1['env_steps'] - c0['env_steps']
-    extra = {'loadflows_per_env_step': (c1['loadflows'] - c0['loadflows']) / max(steps_done, 1),
-             'fd_iterations_per_loadflow': (c1['fd_iterations'] - c0['fd_iterations']) /
-             max(c1['loadflows'] - c0['loadflows'], 1),
-             'game_over_rate': float(n_done.item()) / (B * args.steps),
-             'max_cascade_depth': c1['max_cascade_depth'], 'threads_per_env': c1['threads_per_env'],
-             'smem_bytes_per_env': c1['smem_bytes_per_env'], 'algorithmic_bytes_per_env_step': A,
-             'warm_l2_value': warm_value, 'wall_s_timed_region': wall}
-    line = {'metric': 'env steps/sec (batched grids)', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': kernel_ms, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+    extra = dict(m['counters'])
+    extra.update({'algorithmic_bytes_per_env_step': m['algorithmic_bytes_per_env_step'],
+                  'warm_l2_value': m['warm_l2_value'], 'wall_s_timed_region': m['wall'],
+                  'result_gather': 'none (one GPU)' if world == 1 else
+                  'step kernels store their reward/done/flag rows into rank 0\'s GPU memory over NVLink (peer mapping); '
+                  'rank 0 copies them to the host one step behind on a side stream; NCCL only for set-up and timing',
+                  'per_rank_ms_per_step': m['per_rank_ms_per_step'],
+                  'per_rank_e2e_d2h_gbs': m['per_rank_e2e_d2h_gbs']})
+    line = {'metric': 'env steps/sec (batched grids)', 'value': m['value'], 'unit': 'env-steps/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': m['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': workload_config(args, extra),
             'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-            'gpu_launches': launches,
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'ppn_step_kernel',
-                         'kernel_ms': kernel_ms}}
+            'e2e': m['e2e'],
+            'gpu_launches': m['launches'],
+            'roofline': m['roofline']}
+    if secondary:
+        line['secondary'] = secondary
     if world == 1 and not args.no_cpu:
         pool, cores = cpu_pool(args.grid)
         v, n, busy = cpu_baseline(pool, cores, 10 ** 9, budget_s=args.cpu_seconds)
@@ -388,7 +487,7 @@ def run_b200(args):
                                           % (cores, args.cpu_seconds, args.grid, n)}
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -401,8 +500,13 @@ def main():
     ap.add_argument('--envs', type=int, default=4096, help='envs per GPU')
     ap.add_argument('--agent', default='nothing', choices=['nothing', 'random'],
                     help="'random': one random node-splitting + one line switch per env and step (BASELINE configs[4])")
+    ap.add_argument('--cascade', action='store_true',
+                    help='synthetic thermal limits that make the cascading-failure loop fire (BASELINE configs[2])')
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the other BASELINE configurations')
+    ap.add_argument('--profile-ranks', default=None, metavar='FILE',
+                    help='append the per-rank timing table (kernel, slowest step, host, end-to-end, PCIe rate) to FILE')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

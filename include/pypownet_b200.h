@@ -165,6 +165,26 @@ int ppn_sparse_selfcheck(int n_sub, int n_line, const int32_t* line_or_sub, cons
  * over NCCL each step: written by the step kernel itself, no packing kernels between step and collective. */
 int ppn_set_result_pack(ppn_env* env, double* pack_dev);
 
+/* Diagnostic: every following ppn_step also writes, per env, trace_dev[e][0..3] = SM clock cycles the env's warp / CTA
+ * spent in the call, load-flows, fast-decoupled iterations, restarts (device memory [n_envs][4] int64; NULL switches it
+ * off).  A step lasts as long as its slowest env: this is the tool that shows which one and why (tools/env_trace.py). */
+int ppn_set_env_trace(ppn_env* env, int64_t* trace_dev);
+
+/* ---- env-sharded runs over the GPUs of one box (the reference is single-process: no counterpart) ----
+ * The packed result rows can be written by the step kernel straight into a buffer on ANOTHER GPU (the collecting rank's)
+ * over NVLink: ppn_peer_alloc creates such a buffer (zero-filled device memory + a 64-byte CUDA IPC handle to hand to the
+ * other processes), ppn_peer_open maps it in a peer process (the pointer + an offset is what ppn_set_result_pack takes),
+ * ppn_peer_signal stores `value` to a 64-bit counter after everything enqueued earlier on `stream` (release, system scope),
+ * ppn_peer_wait blocks `stream` until flags_dev[0..n) are all >= value (acquire; the flags may live on a peer GPU),
+ * ppn_peer_read enqueues a device -> host copy of a peer buffer.  pypownet_b200/sharding.py PeerGather is the host side. */
+int ppn_peer_alloc(int device, uint64_t bytes, void** dev_out, uint8_t* handle_out /* [64] */);
+int ppn_peer_open(int device, const uint8_t* handle /* [64] */, void** dev_out);
+int ppn_peer_close(int device, void* dev_ptr);
+int ppn_peer_free(int device, void* dev_ptr);
+int ppn_peer_signal(int device, uint64_t* flag_dev, uint64_t value, void* stream);
+int ppn_peer_wait(int device, const uint64_t* flags_dev, int n, uint64_t value, void* stream);
+int ppn_peer_read(int device, void* host_dst, const void* dev_src, uint64_t bytes, void* stream);
+
 /* Host-buffer form of ppn_step (what a host-side agent calls, RunEnv.step semantics, environment.py:848-866): the batch
  * is cut into chunks, each chunk runs  actions H2D -> step kernel -> results D2H  on its own stream so that copies overlap
  * the kernels of the other chunks; returns when every result is in the host buffers.  Page-locked buffers
@@ -190,6 +210,9 @@ int ppn_device(const ppn_env* env);
  * [5] kernel launches, [6] shared-memory bytes per env, [7] threads per env, [8] most load-flows and [9] most
  * fast-decoupled iterations spent by one env in one call since the previous ppn_get_counters */
 int ppn_get_counters(ppn_env* env, int64_t* out_host /* [10] */);
+/* how deep the cascading-failure loop of game.py:503-589 went, cumulative over the env-steps played so far:
+ * out_host[d] = env-steps whose cascade saw d rounds with an overflowed line, d = 0..6, out_host[7] = seven or more */
+int ppn_get_cascade_histogram(ppn_env* env, int64_t* out_host /* [8] */);
 const char* ppn_last_error(const ppn_env* env);
 const char* ppn_build_info(void);
 void ppn_destroy(ppn_env* env);

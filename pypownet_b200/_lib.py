@@ -77,6 +77,7 @@ SYMBOLS = {
     'ppn_action_valid': (C.c_int, [VP, VP, VP, VP]),
     'ppn_step_host': (C.c_int, [VP, VP, VP, C.c_int64, VP, VP, VP, VP, C.c_int]),
     'ppn_set_result_pack': (C.c_int, [VP, VP]),
+    'ppn_set_env_trace': (C.c_int, [VP, VP]),
     'ppn_sparse_selfcheck': (C.c_int, [C.c_int, C.c_int, VP, VP, C.c_int, C.c_uint32, VP, VP]),
     'ppn_state_width': (C.c_int, [VP, C.c_int]),
     'ppn_get_state': (C.c_int, [VP, C.c_int, VP, VP]),
@@ -88,6 +89,14 @@ SYMBOLS = {
     'ppn_obs_dynamic_length': (C.c_int, [VP]),
     'ppn_device': (C.c_int, [VP]),
     'ppn_get_counters': (C.c_int, [VP, C.POINTER(C.c_int64)]),
+    'ppn_get_cascade_histogram': (C.c_int, [VP, C.POINTER(C.c_int64)]),
+    'ppn_peer_alloc': (C.c_int, [C.c_int, C.c_uint64, C.POINTER(C.c_void_p), VP]),
+    'ppn_peer_open': (C.c_int, [C.c_int, VP, C.POINTER(C.c_void_p)]),
+    'ppn_peer_close': (C.c_int, [C.c_int, VP]),
+    'ppn_peer_free': (C.c_int, [C.c_int, VP]),
+    'ppn_peer_signal': (C.c_int, [C.c_int, VP, C.c_uint64, VP]),
+    'ppn_peer_wait': (C.c_int, [C.c_int, VP, C.c_int, C.c_uint64, VP]),
+    'ppn_peer_read': (C.c_int, [C.c_int, VP, VP, C.c_uint64, VP]),
     'ppn_last_error': (C.c_char_p, [VP]),
     'ppn_build_info': (C.c_char_p, []),
     'ppn_destroy': (None, [VP]),

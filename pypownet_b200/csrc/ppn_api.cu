@@ -37,6 +37,7 @@ struct ppn_env {
     int sparse = 0;            // solver mode of PpnStepArgs.sparse
     int alt_sparse = 0, alt_mat_cap = 0, alt_env_smem_bytes = 0, alt_tpe = 0;   // plan used once buses may be split
     double* pack_dev = nullptr;   // optional packed result rows written by ppn_step (ppn_set_result_pack)
+    long long* trace_dev = nullptr;   // optional per-env trace rows written by ppn_step (ppn_set_env_trace)
     int* h_split = nullptr;    // page-locked, mapped: the kernel sets it when an env applies a node switch
     int* d_split = nullptr;    // its device alias
     long long ws_dense = 0;
@@ -414,6 +415,8 @@ extern "C" const char* ppn_build_info(void) {
 
 extern "C" const char* ppn_last_error(const ppn_env* env) { return env ? env->err.c_str() : g_err.c_str(); }
 
+static int create_body(const ppn_case* g, const ppn_config* cfg, int n_envs, int device, ppn_env* env);
+
 extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, int device, ppn_env** out) {
     ppn_env* env = nullptr;
     if (!g || !cfg || !out || n_envs <= 0) return fail(nullptr, PPN_E_INVALID, "ppn_create: null argument or n_envs <= 0");
@@ -438,6 +441,18 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     if (g->slack_sub < 0 || g->slack_sub >= S) return fail(nullptr, PPN_E_INVALID, "ppn_create: slack_sub out of range");
     if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, PPN_E_CUDA, "ppn_create: cudaSetDevice failed (no such CUDA device)");
     env = new ppn_env();
+    const int rc = create_body(g, cfg, n_envs, device, env);
+    if (rc != PPN_OK) {   // nothing of a half-built handle survives
+        const std::string msg = env->err;
+        ppn_destroy(env);
+        return fail(nullptr, rc, msg);
+    }
+    *out = env;
+    return PPN_OK;
+}
+
+static int create_body(const ppn_case* g, const ppn_config* cfg, int n_envs, int device, ppn_env* env) {
+    const int S = g->n_sub, G = g->n_gen, L = g->n_load, N = g->n_line;
     env->device = device;
     env->B = n_envs;
     env->S = S; env->G = G; env->L = L; env->N = N; env->NB = 2 * S;
@@ -507,7 +522,7 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
             SparseHost h;
             build_sparse(S, N, lor.data(), lex.data(), perm, f == 1, h);
             // byte offsets of entries / rows are packed into 16 bits
-            if (h.nnz >= 8192 || 8 * h.n >= 32768) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "ppn_create: grid too large for the sparse factor tables"); }
+            if (h.nnz >= 8192 || 8 * h.n >= 32768) { return fail(env, PPN_E_UNSUPPORTED, "ppn_create: grid too large for the sparse factor tables"); }
             PpnDevSparse& d = c.sp[f];
             d.n = h.n; d.nnz = h.nnz; d.n_lev = h.n_lev;
             const int cut = choose_cut(h);
@@ -576,8 +591,8 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     // per thread, three CTAs per SM: IEEE-118 2.14 M env-steps/s against 1.72 M with 256-thread CTAs, two per SM)
     if (tpe == 0) tpe = (NB <= 64) ? 32 : 128;
     if (const char* v = getenv("PPN_TPE")) { if (NB > 64 && (atoi(v) == 128 || atoi(v) == 256)) tpe = atoi(v); }
-    if (tpe != 16 && tpe != 32 && tpe != 128 && tpe != 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env must be 0, 16, 32, 128 or 256"); }
-    if ((tpe == 16 && NB > 32) || (tpe == 32 && NB > 64) || NB > 256) { ppn_destroy(env); return fail(nullptr, PPN_E_INVALID, "threads_per_env too small for this grid (16: <= 16 substations, 32: <= 32, 256: <= 128)"); }
+    if (tpe != 16 && tpe != 32 && tpe != 128 && tpe != 256) { return fail(env, PPN_E_INVALID, "threads_per_env must be 0, 16, 32, 128 or 256"); }
+    if ((tpe == 16 && NB > 32) || (tpe == 32 && NB > 64) || NB > 256) { return fail(env, PPN_E_INVALID, "threads_per_env too small for this grid (16: <= 16 substations, 32: <= 32, 256: <= 128)"); }
     env->tpe = tpe;
     const int fixed = ppn_env_smem_fixed_bytes(S, G, L, N, tpe);
     int max_smem = 0;
@@ -599,7 +614,7 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     env->envs_per_block = tpe == 16 ? 4 : (tpe == 32 ? 2 : 1);   // 64-thread CTAs for the sub-warp / warp kernels
     if (const char* v = getenv("PPN_EPB")) { if (tpe == 32 && atoi(v) >= 1 && atoi(v) <= 2) env->envs_per_block = atoi(v); }
     const int cap_bytes = max_smem / env->envs_per_block - fixed - 64;
-    if (cap_bytes < 0) { ppn_destroy(env); return fail(nullptr, PPN_E_UNSUPPORTED, "grid too large for the shared-memory plan"); }
+    if (cap_bytes < 0) { return fail(env, PPN_E_UNSUPPORTED, "grid too large for the shared-memory plan"); }
     // doubles of shared memory per env for matrices / factors / tables under a given solver mode
     auto plan = [&](int mode) {
         int want = n1 * (n1 | 1) + n2 * (n2 | 1);
@@ -633,9 +648,9 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
         env->alt_env_smem_bytes = fixed_b + env->alt_mat_cap * 8;
     }
     env->ws_stride = worst;
-    env->ws_rows = n_envs;
     env->horizon = cfg->n_timesteps_horizon_maintenance > 0 ? cfg->n_timesteps_horizon_maintenance : 1;
-    CK(cudaMalloc(&env->ws, (size_t)n_envs * worst * sizeof(double)));
+    env->ws_rows = n_envs;
+    CK(cudaMalloc(&env->ws, (size_t)env->ws_rows * worst * sizeof(double)));
     env->allocs.push_back(env->ws);
 
     // ---- per-env state
@@ -651,9 +666,9 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
     CK(cudaMemset(env->st.real, 0, (size_t)n_envs * env->st.rw * sizeof(double)));
     CK(cudaMemset(env->st.topo, 0, (size_t)n_envs * env->st.tw));
     CK(cudaMemset(env->st.cnt, 0, (size_t)n_envs * env->st.cw * sizeof(int32_t)));
-    CK(cudaMalloc(&env->stats, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&env->stats, 16 * sizeof(unsigned long long)));
     env->allocs.push_back(env->stats);
-    CK(cudaMemset(env->stats, 0, 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(env->stats, 0, 16 * sizeof(unsigned long long)));
     CK(cudaMalloc(&env->d_init, (size_t)2 * n_envs * sizeof(int32_t)));
     env->allocs.push_back(env->d_init);
     CK(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
@@ -662,7 +677,6 @@ extern "C" int ppn_create(const ppn_case* g, const ppn_config* cfg, int n_envs, 
         *env->h_split = 0;
         CK(cudaHostGetDevicePointer(&env->d_split, env->h_split, 0));
     }
-    *out = env;
     return PPN_OK;
 }
 
@@ -757,6 +771,8 @@ static int launch(ppn_env* env, PpnStepArgs& a, cudaStream_t s) {
             double* nws = nullptr;
             cudaError_t e2 = cudaMalloc(&nws, (size_t)env->B * a.n_cand * env->ws_stride * sizeof(double));
             if (e2 != cudaSuccess) return fail(env, PPN_E_CUDA, std::string("workspace for simulate: ") + cudaGetErrorString(e2));
+            cudaFree(env->ws);   // synchronises the device: no launch still uses the previous workspace
+            env->allocs.erase(std::remove(env->allocs.begin(), env->allocs.end(), (void*)env->ws), env->allocs.end());
             env->allocs.push_back(nws);
             env->ws = nws; env->ws_rows = (long long)env->B * a.n_cand;
             a.ws = nws;
@@ -812,12 +828,19 @@ extern "C" int ppn_step(ppn_env* env, const uint8_t* act_dev, double* obs_dev, i
     a.mode = PPN_MODE_STEP; a.auto_reset = auto_reset; a.act = act_dev;
     a.obs = obs_dev; a.obs_stride = obs_stride; a.reward = reward_dev; a.done = done_dev; a.flag = flag_dev; a.illegal = illegal_dev;
     a.pack = env->pack_dev;
+    a.trace = env->trace_dev;
     return launch(env, a, (cudaStream_t)stream);
 }
 
 extern "C" int ppn_set_result_pack(ppn_env* env, double* pack_dev) {
     if (!env) return fail(nullptr, PPN_E_INVALID, "ppn_set_result_pack: null handle");
     env->pack_dev = pack_dev;
+    return PPN_OK;
+}
+
+extern "C" int ppn_set_env_trace(ppn_env* env, int64_t* trace_dev) {
+    if (!env) return fail(nullptr, PPN_E_INVALID, "ppn_set_env_trace: null handle");
+    env->trace_dev = reinterpret_cast<long long*>(trace_dev);
     return PPN_OK;
 }
 
@@ -1006,6 +1029,94 @@ extern "C" int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_
     return PPN_OK;
 }
 
+// ------------------------------------------------------------------------------------------- peer memory (NVLink)
+// Env-sharded runs: every rank's step kernel stores its packed result rows (reward[5] | done | flag,
+// ppn_set_result_pack) STRAIGHT into a buffer that lives on the collecting rank's GPU, through a peer mapping of that
+// buffer (CUDA IPC, NVLink / NVSwitch stores) -- compute and "gather" are one kernel, no collective sits between two
+// steps.  A per-rank step counter written after each step (release, system scope) tells the collector which rows are
+// complete; a "consumed" counter read back over NVLink gives the writers flow control over a ring of buffers.
+#define CKD(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(nullptr, PPN_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+extern "C" int ppn_peer_alloc(int device, uint64_t bytes, void** dev_out, uint8_t* handle_out) {
+    if (!dev_out || !handle_out || bytes == 0) return fail(nullptr, PPN_E_INVALID, "ppn_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CKD(cudaSetDevice(device));
+    void* p = nullptr;
+    CKD(cudaMalloc(&p, bytes));
+    CKD(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(nullptr, PPN_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memcpy(handle_out, &h, 64);
+    *dev_out = p;
+    return PPN_OK;
+}
+
+extern "C" int ppn_peer_open(int device, const uint8_t* handle, void** dev_out) {
+    if (!handle || !dev_out) return fail(nullptr, PPN_E_INVALID, "ppn_peer_open: bad arguments");
+    CKD(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CKD(cudaIpcOpenMemHandle(dev_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return PPN_OK;
+}
+
+extern "C" int ppn_peer_close(int device, void* dev_ptr) {
+    CKD(cudaSetDevice(device));
+    CKD(cudaIpcCloseMemHandle(dev_ptr));
+    return PPN_OK;
+}
+
+extern "C" int ppn_peer_free(int device, void* dev_ptr) {
+    CKD(cudaSetDevice(device));
+    CKD(cudaFree(dev_ptr));
+    return PPN_OK;
+}
+
+__global__ void ppn_peer_signal_kernel(unsigned long long* flag, unsigned long long value) {
+    __threadfence_system();   // everything this stream wrote before (the step kernel's rows) is visible first
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+}
+
+__global__ void ppn_peer_wait_kernel(const unsigned long long* flags, int n, unsigned long long value) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        unsigned long long v;
+        while (true) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + i) : "memory");
+            if (v >= value) break;
+            __nanosleep(200);
+        }
+    }
+}
+
+extern "C" int ppn_peer_signal(int device, uint64_t* flag_dev, uint64_t value, void* stream) {
+    if (!flag_dev) return fail(nullptr, PPN_E_INVALID, "ppn_peer_signal: null flag");
+    CKD(cudaSetDevice(device));
+    ppn_peer_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)flag_dev, (unsigned long long)value);
+    CKD(cudaGetLastError());
+    return PPN_OK;
+}
+
+extern "C" int ppn_peer_wait(int device, const uint64_t* flags_dev, int n, uint64_t value, void* stream) {
+    if (!flags_dev || n <= 0) return fail(nullptr, PPN_E_INVALID, "ppn_peer_wait: bad arguments");
+    CKD(cudaSetDevice(device));
+    ppn_peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)flags_dev, n, (unsigned long long)value);
+    CKD(cudaGetLastError());
+    return PPN_OK;
+}
+
+extern "C" int ppn_peer_read(int device, void* host_dst, const void* dev_src, uint64_t bytes, void* stream) {
+    if (!host_dst || !dev_src) return fail(nullptr, PPN_E_INVALID, "ppn_peer_read: null buffer");
+    CKD(cudaSetDevice(device));
+    CKD(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return PPN_OK;
+}
+
 extern "C" int ppn_state_width(const ppn_env* env, int field) {
     if (!env) return PPN_E_INVALID;
     switch (field) {
@@ -1048,6 +1159,15 @@ extern "C" int ppn_action_length(const ppn_env* env) { return env ? env->A : PPN
 extern "C" int ppn_obs_length(const ppn_env* env) { return env ? env->OBS : PPN_E_INVALID; }
 extern "C" int ppn_obs_dynamic_length(const ppn_env* env) { return env ? env->OBSD : PPN_E_INVALID; }
 extern "C" int ppn_device(const ppn_env* env) { return env ? env->device : PPN_E_INVALID; }
+
+extern "C" int ppn_get_cascade_histogram(ppn_env* env, int64_t* out_host) {
+    if (!env || !out_host) return fail(env, PPN_E_INVALID, "ppn_get_cascade_histogram: null argument");
+    CK(cudaSetDevice(env->device));
+    unsigned long long h[8];
+    CK(cudaMemcpy(h, env->stats + 8, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; i++) out_host[i] = (int64_t)h[i];
+    return PPN_OK;
+}
 
 extern "C" int ppn_get_counters(ppn_env* env, int64_t* out_host) {
     if (!env || !out_host) return fail(env, PPN_E_INVALID, "ppn_get_counters: null argument");

@@ -162,6 +162,8 @@ struct PpnStepArgs {
                                 // is a handful of wide parallel steps and no full dense matrix is ever stored
     int mat_cap;                // doubles of shared memory per env for B' and B''
     unsigned long long* stats;  // [8] or NULL
+    long long* trace;           // [rows][4] or NULL: clock cycles, load-flows, fast-decoupled iterations and restarts each
+                                // launch row spent in this call (ppn_set_env_trace: where does a step's time go)
     int* split_flag;            // page-locked host word (device alias) set to 1 when an env applies a node switch:
                                 // tells the host that buses may be split from now on (shared-memory plan), or NULL
 };

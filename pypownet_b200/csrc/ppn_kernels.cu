@@ -1767,6 +1767,7 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
     if (mode == PPN_MODE_GAME_OVER && args.mask && !args.mask[env]) return;
 
     if (tid == 0) e.misc()[3] = -1;   // no sparse index tables staged yet
+    const long long t_begin = args.trace ? clock64() : 0;
     // ---- state in
     if (mode == PPN_MODE_INIT) {
         for (int b = tid; b < NB; b += TPE) { e.vm()[b] = c.bus_vm0[b]; e.va()[b] = c.bus_va0[b]; }
@@ -1977,6 +1978,10 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
         int32_t* cr = st.cnt + (size_t)env * st.cw;
         for (int i = tid; i < 3 * N + S + 4; i += TPE) cr[i] = e.recon()[i];
     }
+    if (args.trace && tid == 0) {
+        long long* tr4 = args.trace + 4 * (size_t)slot;
+        tr4[0] = clock64() - t_begin; tr4[1] = n_lf; tr4[2] = n_it; tr4[3] = n_resets;
+    }
     if (args.stats && tid == 0) {
         atomicAdd(args.stats + 0, (unsigned long long)n_lf);
         atomicAdd(args.stats + 1, (unsigned long long)n_it);
@@ -1985,6 +1990,7 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
         atomicMax(args.stats + 4, (unsigned long long)depth);
         atomicMax(args.stats + 5, (unsigned long long)n_lf);
         atomicMax(args.stats + 6, (unsigned long long)n_it);
+        if (mode == PPN_MODE_STEP) atomicAdd(args.stats + 8 + (depth < 7 ? depth : 7), 1ull);   // cascade-depth histogram
     }
 }
 

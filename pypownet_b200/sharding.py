@@ -51,7 +51,8 @@ def unpack_results(packed):
 
 
 def gather_results(packed, world_size=None, out=None):
-    """All-gather of equally sized packs -> [world * B, 7] on every rank (rank-major = global env order)."""
+    """All-gather of equally sized packs -> [world * B, 7] on every rank, rank-major: rows [r * B, (r + 1) * B) are rank
+    r's envs in its local order (with strided_env_ids sharding, local env k of rank r is global env r + world * k)."""
     if world_size is None:
         world_size = dist.get_world_size() if dist.is_initialized() else 1
     if world_size == 1:
@@ -94,6 +95,8 @@ class PipelinedGather(object):
             self.works[buf] = dist.all_gather_into_tensor(self.gathered[buf], self.packs[buf], async_op=True)
         else:
             self.gathered[buf].copy_(self.packs[buf])
+            if self.step:
+                prev = self.gathered[buf ^ 1]          # one rank: the previous rows are simply the previous buffer
         self.step += 1
         return prev
 
@@ -103,3 +106,109 @@ class PipelinedGather(object):
                 self.works[k].wait()
                 self.works[k] = None
         return self.gathered[(self.step - 1) & 1] if self.step else None
+
+
+class PeerGather(object):
+    """The rewards / dones / flags of every shard on the collecting rank WITHOUT a collective between two steps.
+
+    Rank `root` owns, on its GPU, a ring of `ring` result buffers [world * n_local, 7] float64 plus one step counter per
+    rank and a `consumed` counter (ppn_peer_alloc); every other rank maps that memory through CUDA IPC (ppn_peer_open;
+    the 64-byte handle travels once through torch.distributed).  Step t of rank r:
+
+        before_step(t)   r != root: wait (on the GPU, ppn_peer_wait over NVLink) until the ring slot t % ring has been
+                         consumed; point the handle's result pack (ppn_set_result_pack) at rank r's rows of that slot
+        env.step(...)    the step kernel stores its 56-byte rows straight into the root's memory (NVLink stores)
+        after_step(t)    release-store t + 1 into the root's counter of rank r (ppn_peer_signal)
+
+    and on the root, collect(t) -- issued on a side stream, typically one step behind -- waits until all `world`
+    counters reached t + 1, copies the slot into pinned host memory and bumps `consumed`.  The ranks never run in
+    lock-step: a rank can be up to `ring` steps ahead of the slowest one.  world == 1: a local buffer, no waits."""
+
+    FLAG_BYTES = 1024          # the counters sit in front of the ring: [world] step counters, then `consumed` at word 64
+
+    def __init__(self, env, rank, world, root=0, ring=4, group=None):
+        import ctypes as C
+
+        from pypownet_b200 import _lib
+        self.lib = _lib.load()
+        self.env, self.rank, self.world, self.root, self.ring = env, int(rank), int(world), int(root), int(ring)
+        self.n_local = env.n_envs
+        self.device = env.device_index
+        self.slot_doubles = self.world * self.n_local * PACK_WIDTH
+        self.bytes = self.FLAG_BYTES + self.ring * self.slot_doubles * 8
+        self.base = C.c_void_p()
+        self.is_root = self.rank == self.root
+        handle = torch.zeros(64, dtype=torch.uint8)
+        if self.is_root:
+            buf = (C.c_uint8 * 64)()
+            self._ck(self.lib.ppn_peer_alloc(self.device, self.bytes, C.byref(self.base), buf))
+            handle = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        if self.world > 1:
+            h = handle.to(env.device)
+            dist.broadcast(h, src=self.root, group=group)
+            if not self.is_root:
+                hb = (C.c_uint8 * 64).from_buffer_copy(bytes(h.cpu().numpy().tobytes()))
+                self._ck(self.lib.ppn_peer_open(self.device, hb, C.byref(self.base)))
+            dist.barrier(group=group)
+        self.side = torch.cuda.Stream(device=env.device) if self.is_root else None
+        self.host = [torch.empty((self.world * self.n_local, PACK_WIDTH), dtype=torch.float64).pin_memory()
+                     for _ in range(self.ring)] if self.is_root else None
+        self.collected = 0                # steps whose rows the root has copied out
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.ppn_last_error(None)
+            raise RuntimeError('%s (code %d)' % (msg.decode() if msg else 'peer memory call failed', rc))
+
+    def _addr(self, byte_off):
+        import ctypes as C
+        return C.c_void_p(self.base.value + byte_off)
+
+    def _stream(self):
+        import ctypes as C
+        return C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
+
+    def rows_address(self, t):
+        """Device address (on the root's GPU) of this rank's rows of step t."""
+        slot = t % self.ring
+        return self.base.value + self.FLAG_BYTES + 8 * (slot * self.slot_doubles + self.rank * self.n_local * PACK_WIDTH)
+
+    def before_step(self, t):
+        import ctypes as C
+        if not self.is_root and t >= self.ring:
+            self._ck(self.lib.ppn_peer_wait(self.device, self._addr(8 * 64), 1, t - self.ring + 1, self._stream()))
+        self.env._check(self.lib.ppn_set_result_pack(self.env.handle, C.c_void_p(self.rows_address(t))))
+
+    def after_step(self, t):
+        self._ck(self.lib.ppn_peer_signal(self.device, self._addr(8 * self.rank), t + 1, self._stream()))
+
+    def collect(self, t):
+        """Root only: enqueue, on the side stream, `wait for the rows of step t -> copy to pinned host memory -> mark the
+        slot consumed`.  Returns the pinned tensor (complete after wait_all / a synchronisation of the side stream)."""
+        import ctypes as C
+        if not self.is_root:
+            return None
+        if self.ring > 1 and t >= self.collected + self.ring:
+            raise RuntimeError('collect(%d): the ring of %d buffers has been overrun' % (t, self.ring))
+        s = C.c_void_p(self.side.cuda_stream)
+        slot = t % self.ring
+        self._ck(self.lib.ppn_peer_wait(self.device, self._addr(0), self.world, t + 1, s))
+        self._ck(self.lib.ppn_peer_read(self.device, C.c_void_p(self.host[slot].data_ptr()),
+                                        self._addr(self.FLAG_BYTES + 8 * slot * self.slot_doubles),
+                                        8 * self.slot_doubles, s))
+        self._ck(self.lib.ppn_peer_signal(self.device, self._addr(8 * 64), t + 1, s))
+        self.collected = t + 1
+        return self.host[slot]
+
+    def wait_all(self):
+        if self.side is not None:
+            self.side.synchronize()
+
+    def close(self):
+        if self.base.value:
+            torch.cuda.synchronize(self.env.device)
+            if self.is_root:
+                self.lib.ppn_peer_free(self.device, self.base)
+            else:
+                self.lib.ppn_peer_close(self.device, self.base)
+            self.base.value = None

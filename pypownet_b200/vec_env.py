@@ -257,4 +257,8 @@ class VecRunEnv(object):
         self._check(self.lib.ppn_get_counters(self.handle, out))
         keys = ('loadflows', 'fd_iterations', 'env_steps', 'resets', 'max_cascade_depth', 'kernel_launches',
                 'smem_bytes_per_env', 'threads_per_env', 'max_loadflows_one_env_step', 'max_fd_iterations_one_env_step')
-        return dict(zip(keys, [int(v) for v in out]))
+        d = dict(zip(keys, [int(v) for v in out]))
+        hist = (C.c_int64 * 8)()
+        self._check(self.lib.ppn_get_cascade_histogram(self.handle, hist))
+        d['cascade_depth_histogram'] = [int(v) for v in hist]
+        return d
