@@ -86,9 +86,10 @@ def _cpu_init(grid, counter):
         env_id = counter.value
         counter.value += 1
     case, cfg, chronics, imaps = build_workload(grid)
-    c, r = env_starts(1, 97 * env_id)
+    c, r = shard_starts(4096, 0, 1)                     # one env of the 4096-env GPU batch per process
+    k = (257 * env_id) % 4096
     env = FlatEnv(case, Config(cfg, reward_constant=float(case.n_sub), n_sub=case.n_sub), chronics,
-                  start_id=int(c[0]), thermal_limits=imaps, start_row=int(r[0]))
+                  start_id=int(c[k]), thermal_limits=imaps, start_row=int(r[k]))
     a = np.zeros(case.action_length, dtype=np.uint8)
     for _ in range(5):
         if env.step(a)[2]:
@@ -215,6 +216,7 @@ def workload_config(args, extra):
     cfg = {'workload': workload_name(args.grid, args.envs, args.agent, args.cascade) +
            ' (BASELINE.json configs[1] shape)',
            'grid': args.grid, 'envs_per_gpu': args.envs, 'chronics': '%d synthetic x %d rows' % (N_CHRONICS, N_ROWS),
+           'env_starts': 'local env k: chronic k mod 12, first row spread evenly over the chronic (+97 rows per rank)',
            'solver': 'fast-decoupled XB, tol 1e-6, <=25 it (the reference\'s PF_ALG=2)',
            'l2': 'flushed between timed steps (256 MiB write)', 'parallelism': 'env-sharded, dp%d' % args.gpus}
     if extra:
@@ -278,7 +280,22 @@ class Ctx(object):
         return out.cpu().tolist()
 
 
-def measure(ctx, grid, envs, agent, cascade, steps, warmup, with_e2e=True, sampler=None, profile=False):
+def shard_starts(n_local, rank, world, sharding_mode='spread'):
+    """(start chronic, first row) of the envs of a rank.  'spread' (default): every GPU's batch samples the whole data
+    set (sharding.env_starts_spread) -- the per-GPU workload is statistically the same at 1, 2, 4 and 8 GPUs.  For
+    analysis: 'blocks' = rank r owns the contiguous block [r B, (r+1) B) of a global batch laid out as env e -> chronic
+    e mod 12, row (e // 12) mod 719 (one window of ~341 consecutive rows per GPU); 'strided' = env e -> GPU e mod n of the
+    same global batch.  With those two the slowest env of a step -- which is what a step lasts -- depends on the window a
+    GPU happens to hold (profiles/r2e_sharding_workload_effect.txt)."""
+    from pypownet_b200 import sharding
+    if sharding_mode == 'spread':
+        return sharding.env_starts_spread(N_CHRONICS, N_ROWS, n_local, rank)
+    ids = rank + world * np.arange(int(n_local)) if sharding_mode == 'strided' else rank * int(n_local) + np.arange(int(n_local))
+    return sharding.env_starts_of(N_CHRONICS, N_ROWS, ids)
+
+
+def measure(ctx, grid, envs, agent, cascade, steps, warmup, with_e2e=True, sampler=None, sharding_mode='spread',
+            emulate=None):
     """One workload on this process' GPU (and, under torchrun, on every rank at once: weak scaling).  Returns a dict."""
     torch = ctx.torch
     from pypownet_b200.vec_env import VecRunEnv
@@ -286,8 +303,8 @@ def measure(ctx, grid, envs, agent, cascade, steps, warmup, with_e2e=True, sampl
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
     case, cfg, chronics, imaps = build_workload(grid, cascade=cascade)
     B = envs
-    # weak scaling: the global batch of world * B envs is dealt round-robin, rank r owns envs r, r + world, ...
-    sc, sr = sharding.env_starts_of(N_CHRONICS, N_ROWS, sharding.strided_env_ids(B, rank, world))
+    # weak scaling: B envs per GPU; `emulate` = (rank, world) plays that shard's envs on this GPU alone (analysis)
+    sc, sr = shard_starts(B, emulate[0], emulate[1], sharding_mode) if emulate else shard_starts(B, rank, world, sharding_mode)
     env = VecRunEnv(case, cfg, chronics, B, device=ctx.local, reward_constant=float(case.n_sub), thermal_limits=imaps,
                     start_chronics=sc, start_rows=sr)
     actions = torch.zeros((B, case.action_length), dtype=torch.uint8, device=dev)      # do-nothing agent
@@ -427,7 +444,9 @@ def run_b200(args):
     ctx.barrier()
     world, rank = ctx.world, ctx.rank
     sampler = ClockSampler(ctx.local) if rank == 0 else None
-    m = measure(ctx, args.grid, args.envs, args.agent, args.cascade, args.steps, args.warmup, sampler=sampler)
+    emulate = tuple(int(x) for x in args.emulate_shard.split('/')) if args.emulate_shard else None
+    m = measure(ctx, args.grid, args.envs, args.agent, args.cascade, args.steps, args.warmup, sampler=sampler,
+                sharding_mode=args.sharding, emulate=emulate)
     # ---- the other BASELINE configurations, measured in the same run (fewer steps): configs[2] IEEE-30 with the
     # cascading-failure loop firing, configs[3] IEEE-118 do-nothing, configs[4] IEEE-118 with the random agent.  Under
     # `--gpus 8` configs[3] is 65536 envs and configs[4] 32768 envs over the 8 GPUs.
@@ -439,7 +458,7 @@ def run_b200(args):
                 ('configs[3] default118 AC, 8192 envs per GPU (65536 over 8 GPUs)', 'case118', 8192, 'nothing', False),
                 ('configs[4] default118 AC, random node-split + line-switch, 4096 envs per GPU (32768 over 8 GPUs)',
                  'case118', 4096, 'random', False)):
-            r = measure(ctx, grid, envs, agent, cascade, k, 3, with_e2e=True)
+            r = measure(ctx, grid, envs, agent, cascade, k, 3, with_e2e=True, sharding_mode=args.sharding)
             secondary.append({'workload': name, 'grid': grid, 'envs_per_gpu': envs, 'n_gpus': world, 'steps': k,
                               'value': r['value'], 'unit': 'env-steps/s', 'ms_per_step': r['ms_per_step'],
                               'e2e': r['e2e']['value'], 'roofline_frac': r['roofline']['frac'],
@@ -462,6 +481,9 @@ def run_b200(args):
     extra = dict(m['counters'])
     extra.update({'algorithmic_bytes_per_env_step': m['algorithmic_bytes_per_env_step'],
                   'warm_l2_value': m['warm_l2_value'], 'wall_s_timed_region': m['wall'],
+                  'sharding': 'one GPU' if world == 1 else
+                  {'spread': 'every GPU samples the whole data set (rows spread over the chronics, rank r shifted by 97 r rows)',
+                   'blocks': 'contiguous blocks of the global batch', 'strided': 'round-robin (env e -> GPU e mod n)'}[args.sharding],
                   'result_gather': 'none (one GPU)' if world == 1 else
                   'step kernels store their reward/done/flag rows into rank 0\'s GPU memory over NVLink (peer mapping); '
                   'rank 0 copies them to the host one step behind on a side stream; NCCL only for set-up and timing',
@@ -505,6 +527,10 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='skip the other BASELINE configurations')
+    ap.add_argument('--sharding', default='spread', choices=['spread', 'blocks', 'strided'],
+                    help='which chronic rows the envs of a GPU start on (see shard_starts)')
+    ap.add_argument('--emulate-shard', default=None, metavar='R/W',
+                    help='one GPU plays the envs rank R of a W-GPU run would play (analysis of the workload effect)')
     ap.add_argument('--profile-ranks', default=None, metavar='FILE',
                     help='append the per-rank timing table (kernel, slowest step, host, end-to-end, PCIe rate) to FILE')
     args = ap.parse_args()

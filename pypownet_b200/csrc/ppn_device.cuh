@@ -173,7 +173,7 @@ static inline __host__ __device__ int ppn_env_smem_fixed_bytes(int S, int G, int
     const int NB = 2 * S;
     const int A = G + L + 3 * N;
     const int nw = (tpe + 31) / 32;
-    const int un = 4 * NB > 5 * N ? 4 * NB : 5 * N;     // FD work arrays share storage with the branch results
+    const int un = ((4 * NB > 5 * N ? 4 * NB : 5 * N) + 1) & ~1;   // FD work arrays share storage with the branch results (even: 16-byte pairs behind it)
     int dbl = 8 * NB + un + 4 * N + 2 * L + 4 * G + nw * 2;
     int i32 = 3 * N + S + 4 + nw * 2 + 8;
     int i16 = 2 * N + 4 * NB + G + L + 4 * N;

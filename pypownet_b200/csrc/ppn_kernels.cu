@@ -119,13 +119,16 @@ template <int TPE, class D> struct Env : D {
 #define PPN_DBL(name, expr) __device__ __forceinline__ double* name() const { return reinterpret_cast<double*>(base) + (expr); }
     // U: the fast-decoupled work arrays (P, Q mismatches, Ybus diagonal) share their storage with the branch results
     // (flows, amperes), which are only written once the iteration is over.
-    __device__ __forceinline__ int n_union() const { return 4 * this->NB > 5 * this->N ? 4 * this->NB : 5 * this->N; }
-    PPN_DBL(vm, 0) PPN_DBL(va, this->NB) PPN_DBL(vr, 2 * this->NB) PPN_DBL(vi, 3 * this->NB)
+    __device__ __forceinline__ int n_union() const { return ((4 * this->NB > 5 * this->N ? 4 * this->NB : 5 * this->N) + 1) & ~1; }
+    // vri: rectangular voltages as (re, im) PAIRS, bus b at [2b], [2b+1] -- one 16-byte load per neighbour in the mismatch
+    // gather; the DC path uses the first NB entries as its angle vector (theta)
+    PPN_DBL(vm, 0) PPN_DBL(va, this->NB) PPN_DBL(vri, 2 * this->NB) PPN_DBL(theta, 2 * this->NB)
     PPN_DBL(pin, 4 * this->NB) PPN_DBL(qin, 5 * this->NB) PPN_DBL(cs, 6 * this->NB) PPN_DBL(sn, 7 * this->NB)
     PPN_DBL(P, 8 * this->NB) PPN_DBL(Q, 9 * this->NB) PPN_DBL(ydr, 10 * this->NB) PPN_DBL(ydi, 11 * this->NB)
     PPN_DBL(pf, 8 * this->NB) PPN_DBL(qf, 8 * this->NB + this->N) PPN_DBL(pt, 8 * this->NB + 2 * this->N)
     PPN_DBL(qt, 8 * this->NB + 3 * this->N) PPN_DBL(amp, 8 * this->NB + 4 * this->N)
-    PPN_DBL(eyr, 8 * this->NB + n_union()) PPN_DBL(eyi, 8 * this->NB + n_union() + 2 * this->N)
+    // ey: off-diagonal admittance of every line-end entry as a (re, im) pair, entry k at [2k], [2k+1]
+    PPN_DBL(ey, 8 * this->NB + n_union())
     PPN_DBL(lpd, 8 * this->NB + n_union() + 4 * this->N) PPN_DBL(lqd, 8 * this->NB + n_union() + 4 * this->N + this->L)
     PPN_DBL(gpg, 8 * this->NB + n_union() + 4 * this->N + 2 * this->L)
     PPN_DBL(gqg, 8 * this->NB + n_union() + 4 * this->N + 2 * this->L + this->G)
@@ -795,15 +798,21 @@ template <int TPE> __device__ __forceinline__ void sp_invert(const SpView& sp, c
     env_sync<TPE>(mask);
 }
 
-// dot product of a matrix row with a vector, four independent accumulation chains
+// dot product of a matrix row with a vector, four independent accumulation chains; the vector (16-byte aligned, in
+// shared memory: the mismatch vectors) is read two entries per load
 __device__ __forceinline__ double row_dot(const double* m, const double* x, int n) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const double2* x2 = reinterpret_cast<const double2*>(x);
     int j = 0;
     for (; j + 3 < n; j += 4) {
-        a0 = fma(m[j], x[j], a0); a1 = fma(m[j + 1], x[j + 1], a1);
-        a2 = fma(m[j + 2], x[j + 2], a2); a3 = fma(m[j + 3], x[j + 3], a3);
+        const double2 xa = x2[j >> 1], xb = x2[(j >> 1) + 1];
+        const double m0 = m[j], m1 = m[j + 1], m2 = m[j + 2], m3 = m[j + 3];
+        a0 = fma(m0, xa.x, a0); a1 = fma(m1, xa.y, a1);
+        a2 = fma(m2, xb.x, a2); a3 = fma(m3, xb.y, a3);
     }
-    for (; j < n; j++) a0 = fma(m[j], x[j], a0);
+    if (j < n) a0 = fma(m[j], x[j], a0);
+    if (j + 1 < n) a1 = fma(m[j + 1], x[j + 1], a1);
+    if (j + 2 < n) a2 = fma(m[j + 2], x[j + 2], a2);
     return (a0 + a1) + (a2 + a3);
 }
 
@@ -948,7 +957,7 @@ __device__ __forceinline__ void build_entries(Env<TPE, D>& e, const PpnDevCase& 
             const double* y = c.line_y + 8 * l + (end ? 4 : 2);
             e.eoth()[slot] = end == 0 ? e.tbus()[l] : e.fbus()[l];
             e.eline()[slot] = (short)a;
-            e.eyr()[slot] = y[0]; e.eyi()[slot] = y[1];
+            e.ey()[2 * slot] = y[0]; e.ey()[2 * slot + 1] = y[1];
             n++;
         }
         e.deg()[b] = (uint8_t)n;
@@ -968,15 +977,15 @@ template <int TPE, class D>
 __device__ __forceinline__ void bus_power(const Env<TPE, D>& e, const PpnDevCase& c, int b, double& sr, double& si) {
     PPN_ENTRIES(e, c, b, k0, step)
     const int n = e.deg()[b];
-    const double vr = e.vr()[b], vi = e.vi()[b];
+    const double vr = e.vri()[2 * b], vi = e.vri()[2 * b + 1];
     double ir = e.ydr()[b] * vr - e.ydi()[b] * vi, ii = e.ydr()[b] * vi + e.ydi()[b] * vr;
     double jr = 0.0, ji = 0.0;   // second accumulator pair: two independent chains
 #pragma unroll 2
     for (int q = 0; q < n; q++) {
         const int k = k0 + step * q;
         const int o = e.eoth()[k];
-        const double yr = e.eyr()[k], yi = e.eyi()[k];
-        const double wr = e.vr()[o], wi = e.vi()[o];
+        const double yr = e.ey()[2 * k], yi = e.ey()[2 * k + 1];
+        const double wr = e.vri()[2 * o], wi = e.vri()[2 * o + 1];
         if (q & 1) { jr = fma(yr, wr, fma(-yi, wi, jr)); ji = fma(yr, wi, fma(yi, wr, ji)); }
         else { ir = fma(yr, wr, fma(-yi, wi, ir)); ii = fma(yr, wi, fma(yi, wr, ii)); }
     }
@@ -1064,7 +1073,7 @@ __device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, do
         double* Z1 = spb + 2 * ppn_sp_factor_doubles(sp->n, sp->nnz);
         const SpsFactor s1{saddr(f1.T), saddr(f1.Lv), saddr(f1.dg)}, s2{saddr(f2.T), saddr(f2.Lv), saddr(f2.dg)};
         hyb_factor2<TPE>(*sp->d, sp->tb, s1, s2, Z1, Z1 + sp->d->nt * ldz, ldz, tid);
-        hyb_invert2<TPE>(Z1, Z1 + sp->d->nt * ldz, sp->d->nt, ldz, e.vr(), tid);   // vr | vi: 2 NB doubles of scratch in DC mode
+        hyb_invert2<TPE>(Z1, Z1 + sp->d->nt * ldz, sp->d->nt, ldz, e.vri(), tid);   // vri: 2 NB doubles of scratch in DC mode
         hyb_solve<TPE>(*sp->d, sp->tb, s1.Lv, s1.dg, Z1, ldz, saddr(e.ydr()), tid);
         for (int i = tid; i < n1; i += TPE) e.Q()[i] = e.ydr()[sp->bus_row[e.busp()[i]]];
     } else if (solve_mode) {
@@ -1087,13 +1096,13 @@ __device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, do
     for (int b = tid; b < NB; b += TPE) {
         const int t = e.btype()[b];
         if (t == PPN_BT_ISOLATED) continue;
-        e.vr()[b] = (t == PPN_BT_REF) ? va_ref : e.Q()[e.idxp()[b]];  // vr holds theta in DC mode
+        e.theta()[b] = (t == PPN_BT_REF) ? va_ref : e.Q()[e.idxp()[b]];
     }
     env_sync<TPE>(mask);
     // branch flows, slack production
     for (int l = tid; l < e.N; l += TPE) {
         double p = 0.0;
-        if (e.status()[l]) p = c.line_bdc[l] * (e.vr()[e.fbus()[l]] - e.vr()[e.tbus()[l]]) * c.base_mva;
+        if (e.status()[l]) p = c.line_bdc[l] * (e.theta()[e.fbus()[l]] - e.theta()[e.tbus()[l]]) * c.base_mva;
         e.pf()[l] = p; e.pt()[l] = -p; e.qf()[l] = 0.0; e.qt()[l] = 0.0;
     }
     if (tid == 0) {
@@ -1103,7 +1112,7 @@ __device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, do
         double acc = 0.0;
         for (int q = 0; q < e.deg()[ref]; q++) {
             const int k = k0 + step * q;
-            acc += c.line_bdc[e.eline()[k] >> 1] * (e.vr()[ref] - e.vr()[e.eoth()[k]]);
+            acc += c.line_bdc[e.eline()[k] >> 1] * (e.theta()[ref] - e.theta()[e.eoth()[k]]);
         }
         const int g = c.gen_of_sub[s];
         e.gpg()[g] = e.gpg()[g] + (acc - (e.pin()[ref] - c.bus_ysh_r[ref])) * c.base_mva;
@@ -1112,7 +1121,7 @@ __device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, do
     for (int b = tid; b < NB; b += TPE) {
         if (e.btype()[b] == PPN_BT_ISOLATED) continue;
         e.vm()[b] = 1.0;
-        e.va()[b] = e.vr()[b] * (180.0 / PPN_PI);
+        e.va()[b] = e.theta()[b] * (180.0 / PPN_PI);
     }
     success = true;
     return success;
@@ -1160,7 +1169,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
             const double sc = e.gvg()[g] / hypot(vr, vi);
             vr *= sc; vi *= sc;
         }
-        e.vr()[b] = vr; e.vi()[b] = vi;
+        reinterpret_cast<double2*>(e.vri())[b] = make_double2(vr, vi);
         const double vm = hypot(vr, vi);   // fdpf: Vm = abs(V0), Va = angle(V0)
         r_vm[r] = vm;
         r_rvm[r] = 1.0 / vm;
@@ -1206,11 +1215,11 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
             const int to = e.btype()[o];
             if (!sp) {
                 if (inp && to != PPN_BT_REF) M1[i * ld1 + e.idxp()[o]] -= w;
-                if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= e.eyi()[k];
+                if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= e.ey()[2 * k + 1];
             } else if (row > sp->bus_row[o]) {
                 const int pos = sp->line_pos[sp->full ? 4 * l + 2 * e.onode()[l] + e.enode()[l] : l];
                 if (inp && to != PPN_BT_REF) f1.Lv[pos] -= w;
-                if (ispq && to == PPN_BT_PQ) f2.Lv[pos] -= e.eyi()[k];
+                if (ispq && to == PPN_BT_PQ) f2.Lv[pos] -= e.ey()[2 * k + 1];
             }
         }
         r_ydr[r] = yr; r_ydi[r] = yi;
@@ -1255,12 +1264,12 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                     if (t == PPN_BT_PV || t == PPN_BT_PQ) {
                         r_va[r] -= solve_mode ? e.P()[r_ip[r]] : row_dot(M1 + r_ip[r] * ld1, e.P(), n1);
                         sincos(r_va[r], &r_sn[r], &r_cs[r]);
-                        e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
+                        reinterpret_cast<double2*>(e.vri())[b] = make_double2(r_vm[r] * r_cs[r], r_vm[r] * r_sn[r]);
                     }
                 } else if (t == PPN_BT_PQ) {   // Q iteration: Vm[pq] -= B''^-1 Q
                     r_vm[r] -= solve_mode ? e.Q()[r_iq[r]] : row_dot(M2 + r_iq[r] * ld2, e.Q(), n2);
                     r_rvm[r] = 1.0 / r_vm[r];
-                    e.vr()[b] = r_vm[r] * r_cs[r]; e.vi()[b] = r_vm[r] * r_sn[r];
+                    reinterpret_cast<double2*>(e.vri())[b] = make_double2(r_vm[r] * r_cs[r], r_vm[r] * r_sn[r]);
                 }
             }
             env_sync<TPE>(mask);
@@ -1278,14 +1287,25 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
             const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
             double ir = r_ydr[r] * vr - r_ydi[r] * vi, ii = r_ydr[r] * vi + r_ydi[r] * vr;
             double jr = 0.0, ji = 0.0;
-#pragma unroll 2
-            for (int q = 0; q < r_deg[r]; q++) {
-                const int k = r_k0[r] + r_step[r] * q;
-                const int o = e.eoth()[k];
-                const double yr = e.eyr()[k], yi = e.eyi()[k];
-                const double wr = e.vr()[o], wi = e.vi()[o];
-                if (q & 1) { jr = fma(yr, wr, fma(-yi, wi, jr)); ji = fma(yr, wi, fma(yi, wr, ji)); }
-                else { ir = fma(yr, wr, fma(-yi, wi, ir)); ii = fma(yr, wi, fma(yi, wr, ii)); }
+            {   // even entries accumulate in (ir, ii), odd ones in (jr, ji): two independent chains, one 16-byte load
+                // per admittance and per neighbour voltage
+                const double2* ey2 = reinterpret_cast<const double2*>(e.ey());
+                const double2* v2 = reinterpret_cast<const double2*>(e.vri());
+                const short* eo = e.eoth();
+                const int deg = r_deg[r], st2 = r_step[r];
+                int k = r_k0[r];
+                int q = 0;
+                for (; q + 1 < deg; q += 2, k += 2 * st2) {
+                    const int o0 = eo[k], o1 = eo[k + st2];
+                    const double2 y0 = ey2[k], y1 = ey2[k + st2];
+                    const double2 w0 = v2[o0], w1 = v2[o1];
+                    ir = fma(y0.x, w0.x, fma(-y0.y, w0.y, ir)); ii = fma(y0.x, w0.y, fma(y0.y, w0.x, ii));
+                    jr = fma(y1.x, w1.x, fma(-y1.y, w1.y, jr)); ji = fma(y1.x, w1.y, fma(y1.y, w1.x, ji));
+                }
+                if (q < deg) {
+                    const double2 y0 = ey2[k], w0 = v2[eo[k]];
+                    ir = fma(y0.x, w0.x, fma(-y0.y, w0.y, ir)); ii = fma(y0.x, w0.y, fma(y0.y, w0.x, ii));
+                }
             }
             ir += jr; ii += ji;
             const double sr = vr * ir + vi * ii, si = vi * ir - vr * ii;   // V conj(I)
@@ -1360,8 +1380,8 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                 for (int q = 0; q < r_deg[r]; q++) {
                     const int k = r_k0[r] + r_step[r] * q;
                     const int o = e.eoth()[k];
-                    const double yr = e.eyr()[k], yi = e.eyi()[k];
-                    const double wr = e.vr()[o], wi = e.vi()[o];
+                    const double yr = e.ey()[2 * k], yi = e.ey()[2 * k + 1];
+                    const double wr = e.vri()[2 * o], wi = e.vri()[2 * o + 1];
                     ir = fma(yr, wr, fma(-yi, wi, ir));
                     ii = fma(yr, wi, fma(yi, wr, ii));
                 }
@@ -1388,7 +1408,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         if (e.status()[l]) {
             const double* y = c.line_y + 8 * l;
             const int f = e.fbus()[l], t = e.tbus()[l];
-            const double fr = e.vr()[f], fi = e.vi()[f], tr = e.vr()[t], ti = e.vi()[t];
+            const double fr = e.vri()[2 * f], fi = e.vri()[2 * f + 1], tr = e.vri()[2 * t], ti = e.vri()[2 * t + 1];
             const double ifr = y[0] * fr - y[1] * fi + y[2] * tr - y[3] * ti;
             const double ifi = y[0] * fi + y[1] * fr + y[2] * ti + y[3] * tr;
             const double itr = y[4] * fr - y[5] * fi + y[6] * tr - y[7] * ti;

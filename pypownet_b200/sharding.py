@@ -35,6 +35,22 @@ def env_starts_of(n_chronics, n_rows, env_ids):
     return (e % n_chronics).astype(np.int32), ((e // n_chronics) % max(n_rows - 1, 1)).astype(np.int32)
 
 
+def env_starts_spread(n_chronics, n_rows, n_local, rank=0, rank_offset=97):
+    """Starting chronic / first row of the n_local envs of a rank such that EVERY rank's batch samples the whole data
+    set: local env k plays chronic k mod n_chronics from a row spread evenly over the chronic's rows, and rank r is
+    shifted by r * rank_offset rows.  A step lasts as long as its slowest env, and that is decided by which (chronic,
+    row) pairs the batch holds: with contiguous windows (env_starts) the batch of one GPU can miss or contain the data
+    set's worst chains for hundreds of steps in a row (measured: 0.32 ms against 0.45 ms per step for two windows of the
+    same IEEE-14 chronics), so per-GPU work is not the same on every GPU.  Spread starts make the per-GPU workload
+    statistically identical whatever the number of GPUs -- which is what weak scaling assumes.  Local env 0 of rank 0
+    starts on chronic 0, row 0 (the reference's own starting point)."""
+    k = np.arange(int(n_local))
+    per_chronic = -(-int(n_local) // n_chronics)
+    span = max(n_rows - 1, 1)
+    rows = ((k // n_chronics) * span) // per_chronic + rank * rank_offset
+    return (k % n_chronics).astype(np.int32), (rows % span).astype(np.int32)
+
+
 def pack_results(reward, done, flag, out=None):
     """[B, 7] float64 rows from reward [B,5] f64, done [B] u8, flag [B] i32 (any device)."""
     B = reward.shape[0]

@@ -23,11 +23,14 @@ def test_bench_workload_matches_the_oracle(grid, agent, cascade, n_envs, steps):
     from pypownet_b200.vec_env import VecRunEnv
     case, cfg, chronics, imaps = bench.build_workload(grid, cascade=cascade)
     B = n_envs
-    # a stretch of the global env index space that starts at env 0 (offset 0) plus one far into the batch
-    ids = np.r_[np.arange(B // 2), 2900 + 7 * np.arange(B - B // 2)]
-    from pypownet_b200 import sharding
-    sc, sr = sharding.env_starts_of(bench.N_CHRONICS, bench.N_ROWS, ids)
-    assert sc[0] == 0 and sr[0] == 0
+    # envs of the benchmarked batch (bench.shard_starts, 4096 per GPU): the first ones (env 0 = chronic 0, row 0) plus
+    # a stretch far into the batch, and a few of rank 3 of an 8-GPU run
+    sc0, sr0 = bench.shard_starts(4096, 0, 1)
+    sc3, sr3 = bench.shard_starts(4096, 3, 8)
+    pick = np.r_[np.arange(B // 2), 2900 + 7 * np.arange(B - B // 2 - 4)]
+    sc = np.r_[sc0[pick], sc3[[5, 1700, 2811, 4001]]].astype(np.int32)
+    sr = np.r_[sr0[pick], sr3[[5, 1700, 2811, 4001]]].astype(np.int32)
+    assert sc[0] == 0 and sr[0] == 0 and len(sc) == B
     env = VecRunEnv(case, cfg, chronics, B, device=0, reward_constant=float(case.n_sub), thermal_limits=imaps,
                     start_chronics=sc, start_rows=sr)
     ocfg = Config(cfg, reward_constant=float(case.n_sub), n_sub=case.n_sub)
