@@ -754,7 +754,9 @@ extern "C" int ppn_load_chronics(ppn_env* env, int n_chronics, const ppn_chronic
 }
 
 static int launch(ppn_env* env, PpnStepArgs& a, cudaStream_t s) {
-    const bool alt = env->h_split && *(volatile int*)env->h_split != 0;   // may lag a launch or two: only a plan switch
+    // Second plan (explicit inverses, whole SM per CTA) once buses have been split: only the DC path still needs it -- the AC
+    // path borders the hybrid factor with the few sister buses in use and stays on the small plan, per env and per load-flow
+    const bool alt = env->h_split && env->dcfg.dc && *(volatile int*)env->h_split != 0;   // may lag a launch or two
     a.split_flag = env->d_split;
     const int smem_bytes = alt ? env->alt_env_smem_bytes : env->env_smem_bytes;
     a.ws = env->ws; a.ws_stride = env->ws_stride; a.mat_cap = alt ? env->alt_mat_cap : env->mat_cap; a.stats = env->stats;

@@ -1029,6 +1029,60 @@ __device__ __forceinline__ bool mismatch(Env<TPE, D>& e, const PpnDevCase& c, do
     return !any_open;
 }
 
+// ---- split buses under the hybrid factor: the bordered system -----------------------------------------------------
+// The hybrid factor is built on the U structure (one row per substation: bus s).  When node-splitting actions put
+// elements on sister buses, those few buses (k <= PPN_BORDER_MAX per matrix; one per split substation as a rule) are NOT
+// given rows in the sparse structure -- that would be the two-rows-per-substation F structure, four times the fill and
+// five times the levels -- but border it:   [A B; B^T C] [x; y] = [f; g]   with A the U-structure matrix (identity rows
+// for buses that take no part), C the k x k block of the sister buses and B their couplings to A's rows.  Once per
+// load-flow: W = A^-1 B (k solves with the hybrid factor) and the inverse of the Schur complement C - B^T W; per solve:
+// t = A^-1 f, y = (C - B^T W)^-1 (g - B^T t), x = t - W y.  B is never stored: its entries are the line ends of the
+// sister buses.  Storage (per env, in its slice of the HBM workspace): W1 | W2 (k x n each), S1 | S2 (k x k).
+#define PPN_BORDER_MAX 8
+
+struct Border {
+    double* W[2];     // [PPN_BORDER_MAX][n]  A^-1 B of B' / B''
+    double* Sc[2];    // [PPN_BORDER_MAX][PPN_BORDER_MAX]  C, then the inverse of the Schur complement
+    int k[2];         // sister buses in the system of B' (pv + pq) / B'' (pq)
+    int base[2];      // compact index of the first sister bus: n1 - k1 / n2 - k2
+};
+
+// Gauss-Jordan inverse of a k x k matrix (k <= PPN_BORDER_MAX, row stride PPN_BORDER_MAX) by one warp: lane i keeps row i
+// in registers, the pivot row travels by shuffles.  No pivoting: Schur complements of positive definite matrices.
+__device__ __forceinline__ void border_invert_warp(double* Sm, int k, int lane) {
+    double row[PPN_BORDER_MAX];
+#pragma unroll
+    for (int j = 0; j < PPN_BORDER_MAX; j++) row[j] = (lane < k && j < k) ? Sm[lane * PPN_BORDER_MAX + j] : 0.0;
+#pragma unroll
+    for (int p = 0; p < PPN_BORDER_MAX; p++) {
+        if (p < k) {   // uniform
+            double pr[PPN_BORDER_MAX];
+#pragma unroll
+            for (int j = 0; j < PPN_BORDER_MAX; j++) pr[j] = __shfl_sync(PPN_FULL, row[j], p);
+            const double piv = 1.0 / pr[p];
+            if (lane == p) {
+#pragma unroll
+                for (int j = 0; j < PPN_BORDER_MAX; j++) row[j] = (j == p) ? piv : row[j] * piv;
+            } else {
+                const double ci = row[p] * piv;
+#pragma unroll
+                for (int j = 0; j < PPN_BORDER_MAX; j++) row[j] = (j == p) ? -ci : fma(-ci, pr[j], row[j]);
+            }
+        }
+    }
+    if (lane < k) {
+#pragma unroll
+        for (int j = 0; j < PPN_BORDER_MAX; j++)
+            if (j < k) Sm[lane * PPN_BORDER_MAX + j] = row[j];
+    }
+}
+
+// coupling of a sister bus's line-end entry k (other end o) in matrix m: B' -> -1/x, B'' -> -Im(off-diagonal admittance)
+template <int TPE, class D>
+__device__ __forceinline__ double border_coef(const Env<TPE, D>& e, const PpnDevCase& c, int k, int m) {
+    return m == 0 ? -c.line_bp[e.eline()[k] >> 1] : -e.ey()[2 * k + 1];
+}
+
 // rundcpf on the prepared env: B theta = Pbus on pv+pq, Vm := 1.  M1 = n1 x n1 work matrix.
 template <int TPE, int MAXR, class D>
 __device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, double* M1, int n1, int ld1, int ref,
@@ -1133,7 +1187,7 @@ __device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, do
 template <int TPE, int MAXR, class D, bool SMEM>
 __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevCfg& cfg, double* M1, double* M2,
                                          int n1, int n2, int ld1, int ld2, int ref, int slot, int& n_iter,
-                                         const SpView* sp, double* spb, bool solve_mode) {
+                                         const SpView* sp, double* spb, bool solve_mode, Border* bd = nullptr) {
     const int NB = e.NB, S = e.S, tid = e.tid;
     const unsigned mask = e.mask;
     bool success;
@@ -1182,6 +1236,30 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         r_step[r] = b >= S ? -1 : 1;
         r_k0[r] = b >= S ? c.adj_ptr[s + 1] - 1 : c.adj_ptr[s];
     }
+    if (bd) {
+        // sister buses of the bordered system: their entries of the solve vectors sit behind the factor's rows, in
+        // bus order (= the order of their compact indices: sisters come last in the bus array)
+        int c1 = 0, c2 = 0;
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const int b = tid + r * TPE;
+            if (b >= S && b < NB) { c1 += (r_t[r] == PPN_BT_PV || r_t[r] == PPN_BT_PQ); c2 += (r_t[r] == PPN_BT_PQ); }
+        }
+        bd->k[0] = env_sum_int<TPE>(c1, e.redi(), tid, mask);
+        bd->k[1] = env_sum_int<TPE>(c2, e.redi() + Env<TPE, D>::NW, tid, mask);
+        bd->base[0] = n1 - bd->k[0]; bd->base[1] = n2 - bd->k[1];
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const int b = tid + r * TPE;
+            if (b >= S && b < NB) {
+                if (r_t[r] == PPN_BT_PV || r_t[r] == PPN_BT_PQ) r_ip[r] = sp->n + (int)e.idxp()[b] - bd->base[0];
+                if (r_t[r] == PPN_BT_PQ) r_iq[r] = sp->n + (int)e.idxq()[b] - bd->base[1];
+            }
+        }
+        for (int i = tid; i < bd->k[0] * sp->n; i += TPE) bd->W[0][i] = 0.0;
+        for (int i = tid; i < bd->k[1] * sp->n; i += TPE) bd->W[1][i] = 0.0;
+        for (int i = tid; i < PPN_BORDER_MAX * PPN_BORDER_MAX; i += TPE) { bd->Sc[0][i] = 0.0; bd->Sc[1][i] = 0.0; }
+    }
     PPN_TICK(5);
     // B' (r = 0, no charging, no shunts, unit taps) over pv+pq; B'' = -Im(Ybus) over pq; Ybus diagonal
     // dense: assembled in place in M1 / M2; sparse: lower triangle into the static pattern, each entry written by the
@@ -1216,6 +1294,16 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
             if (!sp) {
                 if (inp && to != PPN_BT_REF) M1[i * ld1 + e.idxp()[o]] -= w;
                 if (ispq && to == PPN_BT_PQ) M2[iq * ld2 + e.idxq()[o]] -= e.ey()[2 * k + 1];
+            } else if (bd && (b >= S || o >= S)) {
+                // bordered system: entries of B are written by the owner of the real bus (column = the sister), entries
+                // of C by the owner of the sister bus that is the row
+                if (b < S) {
+                    if (inp && to != PPN_BT_REF) bd->W[0][((int)e.idxp()[o] - bd->base[0]) * sp->n + row] -= w;
+                    if (ispq && to == PPN_BT_PQ) bd->W[1][((int)e.idxq()[o] - bd->base[1]) * sp->n + row] -= e.ey()[2 * k + 1];
+                } else if (o >= S) {
+                    if (inp && to != PPN_BT_REF) bd->Sc[0][(i - sp->n) * PPN_BORDER_MAX + ((int)e.idxp()[o] - bd->base[0])] -= w;
+                    if (ispq && to == PPN_BT_PQ) bd->Sc[1][(iq - sp->n) * PPN_BORDER_MAX + ((int)e.idxq()[o] - bd->base[1])] -= e.ey()[2 * k + 1];
+                }
             } else if (row > sp->bus_row[o]) {
                 const int pos = sp->line_pos[sp->full ? 4 * l + 2 * e.onode()[l] + e.enode()[l] : l];
                 if (inp && to != PPN_BT_REF) f1.Lv[pos] -= w;
@@ -1226,6 +1314,9 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         if (!sp) {
             if (inp) M1[i * ld1 + i] += d1;
             if (ispq) M2[iq * ld2 + iq] += -yi;
+        } else if (bd && b >= S) {
+            if (inp) bd->Sc[0][(i - sp->n) * PPN_BORDER_MAX + (i - sp->n)] += d1;
+            if (ispq) bd->Sc[1][(iq - sp->n) * PPN_BORDER_MAX + (iq - sp->n)] += -yi;
         } else {
             if (inp) { f1.dg[row] = d1; f1.cp[row] = (short)e.idxp()[b]; }
             if (ispq) { f2.dg[row] = -yi; f2.cp[row] = (short)e.idxq()[b]; }
@@ -1251,6 +1342,38 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                     const int ldz = sp->d->nt | 1;
                     const double* Zh = spb + 2 * ppn_sp_factor_doubles(sp->n, sp->nnz) + ((half & 1) ? 0 : sp->d->nt * ldz);
                     hyb_solve<TPE>(*sp->d, sp->tb, saddr(fh.Lv), saddr(fh.dg), Zh, ldz, saddr(wh), tid);
+                    const int m = (half & 1) ? 0 : 1;
+                    if (bd && bd->k[m] > 0) {   // y = S^-1 (g - B^T t), x = t - W y
+                        const int nU = sp->n, kh = bd->k[m];
+#pragma unroll
+                        for (int r = 0; r < RB; r++) {
+                            const int b = tid + r * TPE, t = r_t[r];
+                            if (b < S || b >= NB || !(m == 0 ? (t == PPN_BT_PV || t == PPN_BT_PQ) : t == PPN_BT_PQ)) continue;
+                            const int iw = m == 0 ? r_ip[r] : r_iq[r];
+                            double acc = wh[iw];
+                            for (int q = 0; q < r_deg[r]; q++) {
+                                const int k = r_k0[r] + r_step[r] * q;
+                                const int o = e.eoth()[k];
+                                const int to = e.btype()[o];
+                                if (o < S && (m == 0 ? to != PPN_BT_REF : to == PPN_BT_PQ))
+                                    acc = fma(-border_coef(e, c, k, m), wh[sp->bus_row[o]], acc);
+                            }
+                            wh[iw] = acc;
+                        }
+                        __syncthreads();
+                        double y = 0.0;
+                        if (tid < kh)
+                            for (int j = 0; j < kh; j++) y = fma(bd->Sc[m][tid * PPN_BORDER_MAX + j], wh[nU + j], y);
+                        __syncthreads();
+                        if (tid < kh) wh[nU + tid] = y;
+                        __syncthreads();
+                        for (int i = tid; i < nU; i += TPE) {
+                            double acc = wh[i];
+                            for (int j = 0; j < kh; j++) acc = fma(-bd->W[m][j * nU + i], wh[nU + j], acc);
+                            wh[i] = acc;
+                        }
+                        __syncthreads();
+                    }
                 }
                 else if (TPE > 32 && sp->tb) sps_solve<TPE>(*sp->d, sp->tb, saddr(fh.Lv), saddr(fh.dg), saddr(wh), tid);
                 else sp_solve<TPE>(*sp, fh, wh, tid, mask);
@@ -1334,6 +1457,47 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                                  SpsFactor{saddr(f2.T), saddr(f2.Lv), saddr(f2.dg)}, Z1, Z1 + sp->d->nt * ldz, ldz, tid);
                 PPN_TICK(8);
                 hyb_invert2<TPE>(Z1, Z1 + sp->d->nt * ldz, sp->d->nt, ldz, e.ydr(), tid);   // ydr | ydi: 2 NB doubles, the Ybus diagonal lives in registers here
+                if (bd && (bd->k[0] | bd->k[1])) {
+                    // W = A^-1 B column by column (the solve works on a vector in shared memory: ydr is free here), then
+                    // the Schur complements C - B^T W row by row (owner of the sister bus) and their inverses
+                    const int nU = sp->n;
+                    double* col = e.ydr();
+                    for (int m = 0; m < 2; m++) {
+                        const SpFactor& fm = m == 0 ? f1 : f2;
+                        const double* Zm = Z1 + (m == 0 ? 0 : sp->d->nt * ldz);
+                        for (int j = 0; j < bd->k[m]; j++) {
+                            for (int i = tid; i < nU; i += TPE) col[i] = bd->W[m][j * nU + i];
+                            __syncthreads();
+                            hyb_solve<TPE>(*sp->d, sp->tb, saddr(fm.Lv), saddr(fm.dg), Zm, ldz, saddr(col), tid);
+                            for (int i = tid; i < nU; i += TPE) bd->W[m][j * nU + i] = col[i];
+                            __syncthreads();
+                        }
+                    }
+                    __threadfence_block();
+#pragma unroll
+                    for (int r = 0; r < RB; r++) {
+                        const int b = tid + r * TPE, t = r_t[r];
+                        if (b < S || b >= NB) continue;
+                        for (int m = 0; m < 2; m++) {
+                            if (!(m == 0 ? (t == PPN_BT_PV || t == PPN_BT_PQ) : t == PPN_BT_PQ)) continue;
+                            const int ib = (m == 0 ? r_ip[r] : r_iq[r]) - nU;
+                            for (int j = 0; j < bd->k[m]; j++) {
+                                double acc = bd->Sc[m][ib * PPN_BORDER_MAX + j];
+                                for (int q = 0; q < r_deg[r]; q++) {
+                                    const int k = r_k0[r] + r_step[r] * q;
+                                    const int o = e.eoth()[k];
+                                    const int to = e.btype()[o];
+                                    if (o < S && (m == 0 ? to != PPN_BT_REF : to == PPN_BT_PQ))
+                                        acc = fma(-border_coef(e, c, k, m), bd->W[m][j * nU + sp->bus_row[o]], acc);
+                                }
+                                bd->Sc[m][ib * PPN_BORDER_MAX + j] = acc;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (tid < 64) border_invert_warp(bd->Sc[tid >> 5], bd->k[tid >> 5], tid & 31);
+                    __syncthreads();
+                }
             } else if (sp) {
                 if (TPE > 32 && sp->tb)
                     sps_factor2<TPE>(*sp->d, sp->tb, SpsFactor{saddr(f1.T), saddr(f1.Lv), saddr(f1.dg)},
@@ -1533,9 +1697,15 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
     if (args.sparse) {
         // sparse LDL^T on the static pattern (U while no sister bus is in use, else F), then explicit inverses with
         // one landing row each; the factor storage sits behind the inverses when shared memory has room for it
-        bool split = false;
-        for (int b = S + tid; b < NB; b += TPE) split |= e.btype()[b] != PPN_BT_ISOLATED;
-        const int which = env_any<TPE>(split, mask) ? 1 : 0;
+        int n_sis = 0;
+        for (int b = S + tid; b < NB; b += TPE) n_sis += e.btype()[b] != PPN_BT_ISOLATED;
+        n_sis = env_sum_int<TPE>(n_sis, e.redi(), tid, mask);
+        // hybrid factor, AC: a handful of sister buses border the one-row-per-substation factor (see Border) instead of
+        // moving the env to the two-rows-per-substation structure
+        const bool bordered = TPE > 32 && args.sparse == 3 && !cfg.dc && n_sis > 0 && n_sis <= PPN_BORDER_MAX &&
+                              2 * ppn_sp_factor_doubles(c.sp[0].n, c.sp[0].nnz) + 2 * c.sp[0].nt * (c.sp[0].nt | 1) + c.sp[0].blob_words / 2 <= args.mat_cap &&
+                              2 * PPN_BORDER_MAX * c.sp[0].n + 2 * PPN_BORDER_MAX * PPN_BORDER_MAX <= args.ws_stride;   // the hybrid plan is in place
+        const int which = (n_sis > 0 && !bordered) ? 1 : 0;
         const PpnDevSparse& spd = c.sp[which];
         const bool solve_mode = args.sparse >= 2;
         const int dense_need = solve_mode ? 0 : (n1 + 1) * ld1 + (cfg.dc ? 0 : (n2 + 1) * ld2);
@@ -1567,8 +1737,15 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
         if (dense_need <= args.mat_cap) {
             double* M1 = e.mat();
             double* spb = dense_need + val_need <= args.mat_cap ? M1 + dense_need : wsrow + args.ws_dense;
+            Border bd;
+            if (bordered && spv.hyb) {   // border storage: the env's slice of the workspace (unused by the hybrid plan)
+                bd.W[0] = wsrow; bd.W[1] = wsrow + PPN_BORDER_MAX * spd.n;
+                bd.Sc[0] = wsrow + 2 * PPN_BORDER_MAX * spd.n; bd.Sc[1] = bd.Sc[0] + PPN_BORDER_MAX * PPN_BORDER_MAX;
+                bd.k[0] = bd.k[1] = bd.base[0] = bd.base[1] = 0;
+            }
             success = cfg.dc ? dc_solve<TPE, MAXR, D>(e, c, M1, n1, ld1, ref, sp, spb, solve_mode)
-                             : ac_solve<TPE, MAXR, D, true>(e, c, cfg, M1, M1 + (n1 + 1) * ld1, n1, n2, ld1, ld2, ref, slot, n_iter, sp, spb, solve_mode);
+                             : ac_solve<TPE, MAXR, D, true>(e, c, cfg, M1, M1 + (n1 + 1) * ld1, n1, n2, ld1, ld2, ref, slot, n_iter, sp, spb, solve_mode,
+                                                            (bordered && spv.hyb) ? &bd : nullptr);
         } else {
             double* M1 = wsrow;
             double* spb = wsrow + args.ws_dense;
