@@ -93,6 +93,8 @@ typedef struct ppn_config {
     double reward_constant;              /* `constant` of the shipped CustomRewardSignal (14 / 30 / 118) */
     uint64_t seed;                       /* loop_mode 1 only */
     int32_t threads_per_env;             /* 0 = automatic (one warp per env up to 32 substations, else one CTA of 128 threads); 16, 32, 128 or 256 */
+    int32_t pf_alg;                      /* PYPOWER's PF_ALG for AC: 0 or 2 = fast-decoupled XB (what the reference runs, grid.py:63);
+                                            1 = Newton-Raphson (newtonpf, PF_MAX_IT 10, same pf_tol) -- an option the reference does not use */
 } ppn_config;
 
 /* One chronic (chronic.py:174-246): float32 tables with n_rows rows, planned tables ALREADY shifted by one row. */

@@ -67,6 +67,10 @@ class Config(object):
         self.hard_mode = game_over_mode == 'hard'
         self.loop_mode = loop_mode
         self.tol, self.max_it = 1e-6, 25                               # grid.py:63
+        # PF_ALG: 2 = fast-decoupled XB (what the reference runs, grid.py:63); 1 = Newton-Raphson (north star's named
+        # variant; PYPOWER newtonpf, PF_MAX_IT = 10) -- selected by an extra `pf_alg` key, absent from the shipped configs
+        self.pf_alg = int(cfg.get('pf_alg', 2))
+        self.max_it_nr = 10
         self.reward_constant = float(reward_constant if reward_constant is not None else (n_sub or 0))
 
 
@@ -372,6 +376,8 @@ class FlatEnv(object):
             P, Q, nP, nQ = mismatch(V, Vm)
             tol = self.cfg.tol
             success = bool(nP < tol and nQ < tol)
+            if self.cfg.pf_alg == 1:
+                V, success, self.last_iterations = self._newton(Ybus, Sbus, V0, pv, pq)
             with np.errstate(all='ignore'):
                 import warnings
                 with warnings.catch_warnings():
@@ -379,7 +385,7 @@ class FlatEnv(object):
                     lup = scipy.linalg.lu_factor(Bp[np.ix_(pvpq, pvpq)], check_finite=False)
                     lupp = scipy.linalg.lu_factor(Bpp[np.ix_(pq, pq)], check_finite=False)
                 i = 0
-                while not success and i < self.cfg.max_it:
+                while self.cfg.pf_alg != 1 and not success and i < self.cfg.max_it:
                     i += 1
                     Va[pvpq] = Va[pvpq] - scipy.linalg.lu_solve(lup, P, check_finite=False)
                     V = Vm * np.exp(1j * Va)
@@ -393,7 +399,8 @@ class FlatEnv(object):
                     if nP < tol and nQ < tol:
                         success = True
                         break
-                self.last_iterations = i
+                if self.cfg.pf_alg != 1:
+                    self.last_iterations = i
                 # pfsoln
                 vm = abs(V)
                 va = np.angle(V) * 180 / np.pi
@@ -425,6 +432,43 @@ class FlatEnv(object):
                 return bool(np.isnan(x).any() or np.any(x > 1e10))
             nan = bad(self.vm) or bad(self.va) or bad(self.flows) or bad(self.pd)
         return (not success) or nan
+
+    def _newton(self, Ybus, Sbus, V0, pv, pq):
+        """PYPOWER newtonpf (PF_ALG = 1; restated in oracle/shims/pypower/api.py:_newtonpf and SURVEY.md Appendix A):
+        F = [Re mis[pv]; Re mis[pq]; Im mis[pq]], mis = V conj(Ybus V) - Sbus; J from dSbus_dV; tol on |F|_inf, 10 it."""
+        tol, max_it = self.cfg.tol, self.cfg.max_it_nr
+        V = V0.copy()
+        Va, Vm = np.angle(V), abs(V)
+        pvpq = np.r_[pv, pq]
+        npv, npq = len(pv), len(pq)
+
+        def F_of(V):
+            mis = V * np.conj(Ybus @ V) - Sbus
+            return np.r_[mis[pv].real, mis[pq].real, mis[pq].imag]
+        F = F_of(V)
+        converged = bool(np.max(np.abs(F)) < tol)
+        i = 0
+        with np.errstate(all='ignore'):
+            while not converged and i < max_it:
+                i += 1
+                Ibus = Ybus @ V
+                Vn = V / abs(V)
+                dS_dVm = np.diag(V) @ np.conj(Ybus @ np.diag(Vn)) + np.conj(np.diag(Ibus)) @ np.diag(Vn)
+                dS_dVa = 1j * np.diag(V) @ np.conj(np.diag(Ibus) - Ybus @ np.diag(V))
+                J = np.block([[dS_dVa[np.ix_(pvpq, pvpq)].real, dS_dVm[np.ix_(pvpq, pq)].real],
+                              [dS_dVa[np.ix_(pq, pvpq)].imag, dS_dVm[np.ix_(pq, pq)].imag]])
+                try:
+                    dx = -np.linalg.solve(J, F)
+                except np.linalg.LinAlgError:
+                    dx = np.full(len(F), np.nan)
+                Va[pv] = Va[pv] + dx[:npv]
+                Va[pq] = Va[pq] + dx[npv:npv + npq]
+                Vm[pq] = Vm[pq] + dx[npv + npq:]
+                V = Vm * np.exp(1j * Va)
+                Vm, Va = abs(V), np.angle(V)
+                F = F_of(V)
+                converged = bool(np.max(np.abs(F)) < tol)
+        return V, converged, i
 
     def _flows_a(self):
         """grid.py:112-138, 29-36."""

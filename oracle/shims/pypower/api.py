@@ -43,6 +43,11 @@ def ppoption(ppopt=None, **kw):
     if ppopt is not None:
         opt.update(ppopt)
     opt.update(kw)
+    # test harness only: tools/make_golden.py records Newton-Raphson fixtures by forcing the algorithm the unmodified
+    # reference asks for (it hard-codes PF_ALG=2, grid.py:63)
+    import os
+    if os.environ.get('PYPOWNET_SHIM_PF_ALG'):
+        opt['PF_ALG'] = int(os.environ['PYPOWNET_SHIM_PF_ALG'])
     return opt
 
 

@@ -53,7 +53,7 @@ class PpnConfig(C.Structure):
                 ('pf_max_it', C.c_int32),
                 ('reward_constant', C.c_double),
                 ('seed', C.c_uint64),
-                ('threads_per_env', C.c_int32)]
+                ('threads_per_env', C.c_int32), ('pf_alg', C.c_int32)]
 
 
 class PpnChronic(C.Structure):
@@ -198,6 +198,7 @@ def config_struct(cfg, game_over_mode='soft', without_overflow_cutoff=False, loo
     s.reward_constant = float(reward_constant)
     s.seed = int(seed)
     s.threads_per_env = int(threads_per_env)
+    s.pf_alg = int(cfg.get('pf_alg', 2))          # 1: Newton-Raphson (not in the shipped configuration files)
     return s
 
 

@@ -581,6 +581,8 @@ static int create_body(const ppn_case* g, const ppn_config* cfg, int n_envs, int
     k.loop_mode = cfg->loop_mode;
     k.tol = cfg->pf_tol > 0 ? cfg->pf_tol : 1e-6;
     k.max_it = cfg->pf_max_it > 0 ? cfg->pf_max_it : 25;
+    k.alg = cfg->pf_alg == 1 ? 1 : 2;
+    k.max_it_nr = 10;
     k.reward_k = cfg->reward_constant;
     k.seed = cfg->seed;
     k.max_reset_attempts = 64;
@@ -610,7 +612,8 @@ static int create_body(const ppn_case* g, const ppn_config* cfg, int n_envs, int
     if (env->sparse == 3 && (env->dc.sp[0].nt > 40 || env->dc.sp[1].nt > 40)) env->sparse = 1;   // hyb_invert2 tiles hold <= 40 rows
     if (const char* v = getenv("PPN_SPARSE")) env->sparse = atoi(v);
     env->ws_dense = 2LL * NB * (NB | 1);
-    const int worst = (int)env->ws_dense + env->sp_need[1] + env->sp_blob_dbl[1];
+    int worst = (int)env->ws_dense + env->sp_need[1] + env->sp_blob_dbl[1];
+    if (cfg->pf_alg == 1 && worst < 2 * NB * (2 * NB + 1)) worst = 2 * NB * (2 * NB + 1);   // the Newton-Raphson Jacobian + right-hand side
     env->envs_per_block = tpe == 16 ? 4 : (tpe == 32 ? 2 : 1);   // 64-thread CTAs for the sub-warp / warp kernels
     if (const char* v = getenv("PPN_EPB")) { if (tpe == 32 && atoi(v) >= 1 && atoi(v) <= 2) env->envs_per_block = atoi(v); }
     const int cap_bytes = max_smem / env->envs_per_block - fixed - 64;
@@ -620,6 +623,10 @@ static int create_body(const ppn_case* g, const ppn_config* cfg, int n_envs, int
         int want = n1 * (n1 | 1) + n2 * (n2 | 1);
         if (mode == 1) want = (n1 + 1) * (n1 | 1) + (n2 + 1) * (n2 | 1) + env->sp_need[0] + env->sp_blob_dbl[0];
         if (mode >= 2) want = env->sp_need[0] + env->sp_blob_dbl[0];
+        if (cfg->pf_alg == 1 && tpe <= 32) {   // Newton-Raphson: the Jacobian of the un-split grid + right-hand side
+            const int nj = n1 + n2;
+            if (want < nj * (nj + 1)) want = nj * (nj + 1);
+        }
         want = (want + 3) & ~1;   // the capacity below is rounded down to an even number of doubles
         if (want > worst) want = worst;
         int cap = cap_bytes / 8;

@@ -121,6 +121,8 @@ struct PpnDevCfg {
     int hard_mode, loop_mode;
     double tol;
     int max_it;
+    int alg;          // 2 (or 0): fast-decoupled XB, what the reference runs; 1: Newton-Raphson
+    int max_it_nr;    // PYPOWER's PF_MAX_IT (10)
     double reward_k;
     unsigned long long seed;
     int max_reset_attempts;

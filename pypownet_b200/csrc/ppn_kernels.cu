@@ -80,6 +80,18 @@ template <int TPE> __device__ __forceinline__ int env_sum_int(int v, int* red, i
     return r;
 }
 
+template <int TPE> __device__ __forceinline__ int env_min_int(int v, int* red, int tid, unsigned mask) {
+    v = __reduce_min_sync(TPE <= 32 ? mask : PPN_FULL, v);
+    if (TPE <= 32) return v;
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    int r = red[0];
+#pragma unroll
+    for (int k = 1; k < (TPE + 31) / 32; k++) r = min(r, red[k]);
+    return r;
+}
+
 template <int TPE> __device__ __forceinline__ double env_sum_double(double v, double* red, int tid, unsigned mask) {
 #pragma unroll
     for (int o = (TPE < 32 ? TPE : 32) / 2; o > 0; o >>= 1) v += __shfl_xor_sync(TPE <= 32 ? mask : PPN_FULL, v, o);
@@ -1585,6 +1597,234 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
     return success;
 }
 
+// ---- Newton-Raphson (PF_ALG = 1): the north star's named solver; the reference itself runs the fast-decoupled one -----
+// Dense system A x = b, A n x n with the right-hand side in column n (row stride ld), Gaussian elimination with partial
+// pivoting, one row per thread in the elimination.  The matrix lives in shared memory when the handle's plan has room
+// for it (warp-per-env grids: IEEE-14 22 x 23, IEEE-30 53 x 54 doubles), else in the env's slice of the HBM workspace
+// (an IEEE-118 Jacobian is 181 x 181 = 262 KB; this solver is an option, not the benchmarked path).
+// Returns false on an exactly singular matrix (PYPOWER's spsolve then yields NaN: the iteration never converges).
+template <int TPE>
+__device__ __forceinline__ bool dense_solve_pivot(double* A, int n, int ld, int tid, unsigned mask, double* redd, int* redi) {
+    for (int k = 0; k < n; k++) {
+        double best = -1.0;
+        int bi = 0x7fffffff;
+        for (int i = k + tid; i < n; i += TPE) {
+            const double v = fabs(A[(size_t)i * ld + k]);
+            if (v > best) { best = v; bi = i; }
+        }
+        const double vmax = env_max_nan<TPE>(best, redd, tid, mask);
+        if (!(vmax > 0.0)) return false;   // zero or NaN column
+        const int p = env_min_int<TPE>(best == vmax ? bi : 0x7fffffff, redi, tid, mask);
+        if (p != k)
+            for (int j = k + tid; j <= n; j += TPE) {
+                const double a = A[(size_t)k * ld + j], b = A[(size_t)p * ld + j];
+                A[(size_t)k * ld + j] = b; A[(size_t)p * ld + j] = a;
+            }
+        env_sync<TPE>(mask);
+        const double rp = 1.0 / A[(size_t)k * ld + k];
+        for (int i = k + 1 + tid; i < n; i += TPE) {
+            double* ai = A + (size_t)i * ld;
+            const double* ak = A + (size_t)k * ld;
+            const double f = ai[k] * rp;
+            if (f != 0.0)
+                for (int j = k + 1; j <= n; j++) ai[j] = fma(-f, ak[j], ai[j]);
+        }
+        env_sync<TPE>(mask);
+    }
+    for (int k = n - 1; k >= 0; k--) {
+        const double xk = A[(size_t)k * ld + n] / A[(size_t)k * ld + k];
+        env_sync<TPE>(mask);
+        if (tid == 0) A[(size_t)k * ld + n] = xk;
+        for (int i = tid; i < k; i += TPE) A[(size_t)i * ld + n] = fma(-A[(size_t)i * ld + k], xk, A[(size_t)i * ld + n]);
+        env_sync<TPE>(mask);
+    }
+    return true;
+}
+
+// runpf with PF_ALG = 1 (PYPOWER newtonpf + pfsoln):
+// F = [Re mis[pv+pq]; Im mis[pq]], mis = V conj(Ybus V) - Sbus; J = [[Re dS/dVa, Re dS/dVm], [Im dS/dVa, Im dS/dVm]]
+// from dSbus_dV; dx = -J^-1 F; tolerance on |F|_inf; at most max_it_nr iterations.  Unknown / equation order: angles
+// of pv+pq buses by compact index idxp, then magnitudes of pq buses by idxq (any consistent order gives the same dx).
+// J: (n1+n2) x (n1+n2+1) doubles in the HBM workspace.
+template <int TPE, class D>
+__device__ __forceinline__ bool nr_solve(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevCfg& cfg, double* J, int n1, int n2,
+                                         int ref, int& n_iter) {
+    const int NB = e.NB, S = e.S, tid = e.tid, nJ = n1 + n2, ld = nJ + 1;
+    const unsigned mask = e.mask;
+    // V0 from the stored state (on-line generators impose their set-point magnitude); va holds RADIANS until the end
+    for (int b = tid; b < NB; b += TPE) {
+        if (e.btype()[b] == PPN_BT_ISOLATED) continue;
+        double sn, cs;
+        sincos(e.va()[b] * (PPN_PI / 180.0), &sn, &cs);
+        double vr = e.vm()[b] * cs, vi = e.vm()[b] * sn;
+        const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
+        const int g = c.gen_of_sub[s];
+        if (g >= 0 && e.gnode()[g] == node && e.gstat()[g] > 0) {
+            const double sc = e.gvg()[g] / hypot(vr, vi);
+            vr *= sc; vi *= sc;
+        }
+        e.vri()[2 * b] = vr; e.vri()[2 * b + 1] = vi;
+        e.vm()[b] = hypot(vr, vi);
+        e.va()[b] = atan2(vi, vr);
+        // Ybus diagonal: shunt + own-end admittances of the in-service lines on this bus
+        PPN_ENTRIES(e, c, b, k0, step)
+        double yr = c.bus_ysh_r[b], yi = c.bus_ysh_i[b];
+        for (int q = 0; q < e.deg()[b]; q++) {
+            const int a = e.eline()[k0 + step * q];
+            const double* y = c.line_y + 8 * (a >> 1) + ((a & 1) ? 6 : 0);
+            yr += y[0]; yi += y[1];
+        }
+        e.ydr()[b] = yr; e.ydi()[b] = yi;
+    }
+    env_sync<TPE>(mask);
+    bool success = false;
+    int it = 0;
+    while (true) {
+        // bus currents (kept for the Jacobian), power mismatch
+        bool open = false;
+        for (int b = tid; b < NB; b += TPE) {
+            const int t = e.btype()[b];
+            if (t == PPN_BT_ISOLATED) continue;
+            PPN_ENTRIES(e, c, b, k0, step)
+            const double vr = e.vri()[2 * b], vi = e.vri()[2 * b + 1];
+            double ir = e.ydr()[b] * vr - e.ydi()[b] * vi, ii = e.ydr()[b] * vi + e.ydi()[b] * vr;
+            for (int q = 0; q < e.deg()[b]; q++) {
+                const int k = k0 + step * q;
+                const int o = e.eoth()[k];
+                const double yr = e.ey()[2 * k], yi = e.ey()[2 * k + 1];
+                const double wr = e.vri()[2 * o], wi = e.vri()[2 * o + 1];
+                ir = fma(yr, wr, fma(-yi, wi, ir));
+                ii = fma(yr, wi, fma(yi, wr, ii));
+            }
+            e.cs()[b] = ir; e.sn()[b] = ii;
+            if (t == PPN_BT_REF) continue;
+            const double fp = (vr * ir + vi * ii) - e.pin()[b];
+            e.P()[e.idxp()[b]] = fp;
+            open |= !(fabs(fp) < cfg.tol);
+            if (t == PPN_BT_PQ) {
+                const double fq = (vi * ir - vr * ii) - e.qin()[b];
+                e.Q()[e.idxq()[b]] = fq;
+                open |= !(fabs(fq) < cfg.tol);
+            }
+        }
+        const bool any_open = env_any<TPE>(open, mask);
+        env_sync<TPE>(mask);
+        if (!any_open) { success = true; break; }
+        if (it == cfg.max_it_nr) break;
+        it++;
+        // Jacobian, one bus (= up to two rows) per thread; right-hand side F
+        for (int i = tid; i < nJ * ld; i += TPE) J[i] = 0.0;
+        env_sync<TPE>(mask);
+        for (int b = tid; b < NB; b += TPE) {
+            const int t = e.btype()[b];
+            if (t != PPN_BT_PV && t != PPN_BT_PQ) continue;
+            const bool ispq = t == PPN_BT_PQ;
+            double* rowp = J + (size_t)e.idxp()[b] * ld;
+            double* rowq = ispq ? J + (size_t)(n1 + e.idxq()[b]) * ld : nullptr;
+            PPN_ENTRIES(e, c, b, k0, step)
+            const double vr = e.vri()[2 * b], vi = e.vri()[2 * b + 1], vm = e.vm()[b];
+            double wr = 0.0, wi = 0.0;   // sum of the off-diagonal terms Y_bo V_o = I_b - Y_bb V_b
+            for (int q = 0; q < e.deg()[b]; q++) {
+                const int k = k0 + step * q;
+                const int o = e.eoth()[k];
+                const int to = e.btype()[o];
+                const double yr = e.ey()[2 * k], yi = e.ey()[2 * k + 1];
+                const double ur = yr * e.vri()[2 * o] - yi * e.vri()[2 * o + 1], ui = yr * e.vri()[2 * o + 1] + yi * e.vri()[2 * o];
+                wr += ur; wi += ui;
+                // T = V_b conj(Y_bo V_o):  dS_b/dVa_o = -j T,  dS_b/dVm_o = T / |V_o|
+                const double tr = vr * ur + vi * ui, ti = vi * ur - vr * ui;
+                if (to == PPN_BT_REF) continue;
+                const int cp = e.idxp()[o];
+                rowp[cp] += ti;
+                if (rowq) rowq[cp] += -tr;
+                if (to == PPN_BT_PQ) {
+                    const int cq = n1 + e.idxq()[o];
+                    const double rvo = 1.0 / e.vm()[o];
+                    rowp[cq] += tr * rvo;
+                    if (rowq) rowq[cq] += ti * rvo;
+                }
+            }
+            // diagonal: dS_b/dVa_b = j V_b conj(I_b - Y_bb V_b),  dS_b/dVm_b = (|V_b|^2 conj(Y_bb) + conj(I_b) V_b) / |V_b|
+            const double xr = vr * wr + vi * wi, xi = vi * wr - vr * wi;
+            const int cp = e.idxp()[b];
+            rowp[cp] += -xi;
+            if (rowq) rowq[cp] += xr;
+            if (ispq) {
+                const double ir = e.cs()[b], ii = e.sn()[b];
+                const double mr = (vm * vm * e.ydr()[b] + (ir * vr + ii * vi)) / vm;
+                const double mi = (-vm * vm * e.ydi()[b] + (ir * vi - ii * vr)) / vm;
+                const int cq = n1 + e.idxq()[b];
+                rowp[cq] += mr;
+                rowq[cq] += mi;
+            }
+            rowp[nJ] = e.P()[e.idxp()[b]];
+            if (rowq) rowq[nJ] = e.Q()[e.idxq()[b]];
+        }
+        env_sync<TPE>(mask);
+        const bool solved = dense_solve_pivot<TPE>(J, nJ, ld, tid, mask, e.redd(), e.redi());
+        // dx = -J^-1 F; V = Vm e^{j Va}; Vm = |V|, Va = angle(V)
+        for (int b = tid; b < NB; b += TPE) {
+            const int t = e.btype()[b];
+            if (t != PPN_BT_PV && t != PPN_BT_PQ) continue;
+            const double nanv = nan("");
+            double va = e.va()[b] - (solved ? J[(size_t)e.idxp()[b] * ld + nJ] : nanv);
+            double vm = e.vm()[b];
+            if (t == PPN_BT_PQ) vm -= solved ? J[(size_t)(n1 + e.idxq()[b]) * ld + nJ] : nanv;
+            double sn, cs;
+            sincos(va, &sn, &cs);
+            const double vr = vm * cs, vi = vm * sn;
+            e.vri()[2 * b] = vr; e.vri()[2 * b + 1] = vi;
+            e.vm()[b] = hypot(vr, vi);
+            e.va()[b] = atan2(vi, vr);
+        }
+        env_sync<TPE>(mask);
+    }
+    n_iter = it;
+    // ---- pfsoln (as the fast-decoupled path): generator Q, the slack's P, bus results, branch flows
+    int n_on = 0;
+    for (int g = tid; g < e.G; g += TPE) n_on += (e.gstat()[g] > 0 && e.btype()[e.gbus()[g]] != PPN_BT_ISOLATED);
+    n_on = env_sum_int<TPE>(n_on, e.redi(), tid, mask);
+    for (int b = tid; b < NB; b += TPE) {
+        const int t = e.btype()[b];
+        if (t == PPN_BT_ISOLATED) continue;
+        const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
+        const int g = c.gen_of_sub[s];
+        const double vr = e.vri()[2 * b], vi = e.vri()[2 * b + 1];
+        if (g >= 0 && e.gnode()[g] == node && e.gstat()[g] > 0) {
+            const double ir = e.cs()[b], ii = e.sn()[b];
+            const double sr = vr * ir + vi * ii, si = vi * ir - vr * ii;
+            double pd, qd;
+            bus_demand(e, c, b, pd, qd);
+            double q = si * c.base_mva + qd;
+            if (n_on > 1) {
+                const double qmin = c.gen_qmin[g], qmax = c.gen_qmax[g];
+                if (qmin != qmax) q = qmin + ((q - qmin) / (qmax - qmin + 2.220446049250313e-16)) * (qmax - qmin);
+            }
+            e.gqg()[g] = q;
+            if (t == PPN_BT_REF) e.gpg()[g] = sr * c.base_mva + pd;
+        }
+        e.vm()[b] = hypot(vr, vi);
+        e.va()[b] = atan2(vi, vr) * (180.0 / PPN_PI);
+    }
+    env_sync<TPE>(mask);   // the branch results below reuse the storage of the mismatch vectors
+    for (int l = tid; l < e.N; l += TPE) {
+        double pf = 0.0, qf = 0.0, pt = 0.0, qt = 0.0;
+        if (e.status()[l]) {
+            const double* y = c.line_y + 8 * l;
+            const int f = e.fbus()[l], t = e.tbus()[l];
+            const double fr = e.vri()[2 * f], fi = e.vri()[2 * f + 1], tr = e.vri()[2 * t], ti = e.vri()[2 * t + 1];
+            const double ifr = y[0] * fr - y[1] * fi + y[2] * tr - y[3] * ti;
+            const double ifi = y[0] * fi + y[1] * fr + y[2] * ti + y[3] * tr;
+            const double itr = y[4] * fr - y[5] * fi + y[6] * tr - y[7] * ti;
+            const double iti = y[4] * fi + y[5] * fr + y[6] * ti + y[7] * tr;
+            pf = (fr * ifr + fi * ifi) * c.base_mva; qf = (fi * ifr - fr * ifi) * c.base_mva;
+            pt = (tr * itr + ti * iti) * c.base_mva; qt = (ti * itr - tr * iti) * c.base_mva;
+        }
+        e.pf()[l] = pf; e.qf()[l] = qf; e.pt()[l] = pt; e.qt()[l] = qt;
+    }
+    return success;
+}
+
 // One load-flow on the current topology/injections (grid.py:244-264 around runpf / rundcpf).  Returns true when the
 // reference raises DivergingLoadflowException.  On success the state (vm, va in degrees, gen pg/qg, flows) is the
 // adopted output (`self.mpc = output`, grid.py:260).
@@ -1694,7 +1934,13 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
     // ---- matrices: shared memory when they fit, else the env's slice of the global workspace
     const int ld1 = n1 | 1, ld2 = n2 | 1;
     bool success;
-    if (args.sparse) {
+    if (!cfg.dc && cfg.alg == 1) {
+        // Newton-Raphson (ppn_config.pf_alg = 1): dense Jacobian in the env's slice of the workspace
+        env_sync<TPE>(mask);
+        const int nJ = n1 + n2;
+        double* Jbuf = nJ * (nJ + 1) <= args.mat_cap ? e.mat() : args.ws + (size_t)slot * args.ws_stride;   // shared memory when it fits
+        success = nr_solve<TPE, D>(e, c, cfg, Jbuf, n1, n2, ref, n_iter);
+    } else if (args.sparse) {
         // sparse LDL^T on the static pattern (U while no sister bus is in use, else F), then explicit inverses with
         // one landing row each; the factor storage sits behind the inverses when shared memory has room for it
         int n_sis = 0;

@@ -41,7 +41,8 @@ class Fixture(object):
         # outcome there is SuperLU rounding noise).  The reference's state after such a step is
         # recorded as state rows (resync_*) and every replay continues from it.
         n = len(self.actions)
-        self.mismatch = z['mismatch'] if 'mismatch' in z.files else np.zeros(n, dtype=bool)
+        # 0: none; 1: done / flag of the step differ; 2: step agrees, only the restart (process_game_over) differs
+        self.mismatch = z['mismatch'].astype(np.int8) if 'mismatch' in z.files else np.zeros(n, dtype=np.int8)
         self.resync = {}
         for k, t in enumerate(np.flatnonzero(self.mismatch)):
             self.resync[int(t)] = (z['resync_real'][k], z['resync_topo'][k], z['resync_cnt'][k])

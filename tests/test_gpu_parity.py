@@ -36,7 +36,7 @@ def test_cuda_reproduces_reference_fixture(name):
     assert np.max(np.abs(obs0[0] - fx.obs0)) < TOL
     worst = 0.0
     for t in range(len(fx.actions)):
-        if fx.mismatch[t]:
+        if fx.mismatch[t] == 1:
             # floating pocket: the reference's outcome is decided by the rounding of a singular
             # SuperLU pivot; the library reports "diverging", and the replay continues from the reference's state
             obs, reward, done, flag = env.step(np.repeat(fx.actions[t][None], B, axis=0))
@@ -55,6 +55,9 @@ def test_cuda_reproduces_reference_fixture(name):
         assert np.all(d == int(fx.done[t])) and np.all(f == int(fx.flag[t])), 'step %d: %s %s' % (t, d, f)
         if fx.default_reward:
             assert np.max(np.abs(reward.cpu().numpy() - fx.reward[t][None])) < TOL, t
+        if fx.mismatch[t] == 2:     # same outcome, but a floating pocket inside the reference's process_game_over
+            set_rows(env, fx.resync[t], B)
+            continue
         if fx.done[t]:
             obs = env.process_game_over(done)
             expect = fx.reset_obs[t]
@@ -67,18 +70,22 @@ def test_cuda_reproduces_reference_fixture(name):
         worst = max(worst, err)
     assert worst < TOL
     print('%s: %d steps replayed, %d floating-pocket mismatches, max |cuda - reference| = %.3g'
-          % (name, len(fx.actions), int(fx.mismatch.sum()), worst))
+          % (name, len(fx.actions), int((fx.mismatch != 0).sum()), worst))
 
 
 @pytest.mark.parametrize('name,steps', [('d14_ac_random', 120), ('d30_ac_random', 60), ('d118_ac_random', 25),
-                                        ('d14_dc_random', 60), ('d118_ac_random:DC', 20), ('d30_ac_random:DC', 30)])
+                                        ('d14_dc_random', 60), ('d118_ac_random:DC', 20), ('d30_ac_random:DC', 30),
+                                        ('d14_ac_random:NR', 80), ('d30_ac_random:NR', 40), ('d118_ac_random:NR', 12)])
 def test_cuda_matches_oracle_on_a_ragged_batch(name, steps):
     """Envs start on different chronics and rows and receive different random actions; auto-reset as Runner does.
-    `:DC` replays a grid's fixture data with loadflow_mode DC (rundcpf through the same sparse / hybrid solvers)."""
+    `:DC` replays a grid's fixture data with loadflow_mode DC (rundcpf through the same sparse / hybrid solvers), `:NR`
+    with the Newton-Raphson solver (the oracle's newtonpf is itself pinned on tests/golden/d*_nr_*.npz)."""
     name, _, mode = name.partition(':')
     fx = Fixture(name)
     if mode == 'DC':
         fx.config = dict(fx.config, loadflow_mode='DC')
+    if mode == 'NR':                                  # Newton-Raphson (ppn_config.pf_alg = 1) against the oracle's newtonpf
+        fx.config = dict(fx.config, pf_alg=1)
     B = 24
     rng = np.random.default_rng(11)
     nch = len(fx.chronics)

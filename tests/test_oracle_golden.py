@@ -29,12 +29,16 @@ def test_oracle_reproduces_reference_trajectory(name):
             if fx.default_reward:
                 assert np.max(np.abs(r - fx.sim_reward[t])) < TOL
         o, r, d, f, _ = env.step(fx.actions[t])
-        if fx.mismatch[t]:
+        if fx.mismatch[t] == 1:
             # floating pocket: the reference's outcome is rounding noise inside SuperLU; the oracle says "diverging"
-            assert d and f == 2, 'step %d' % t
+            # (fast-decoupled) or whatever its own dense solve of the singular system gives (Newton-Raphson)
+            assert fx.config.get('pf_alg', 2) == 1 or (d and f == 2), 'step %d' % t
             env.import_rows(*fx.resync[t])
             continue
         assert (bool(d), int(f)) == (bool(fx.done[t]), int(fx.flag[t])), 'step %d' % t
+        if fx.mismatch[t] == 2:              # same outcome, but a pocket inside process_game_over: restart not compared
+            env.import_rows(*fx.resync[t])
+            continue
         if not d:
             assert np.max(np.abs(o - fx.obs[t][:nd])) < TOL, 'step %d' % t
         if fx.default_reward:
@@ -43,7 +47,7 @@ def test_oracle_reproduces_reference_trajectory(name):
             o = env.process_game_over()
             assert np.max(np.abs(o - fx.reset_obs[t][:nd])) < TOL, 'reset %d' % t
     assert np.max(np.abs(env.observation_static() - fx.obs0[nd:])) == 0
-    print('%s: %d steps, %d floating-pocket mismatches' % (name, len(fx.actions), int(fx.mismatch.sum())))
+    print('%s: %d steps, %d floating-pocket mismatches' % (name, len(fx.actions), int((fx.mismatch != 0).sum())))
 
 
 def test_baseline_config0_replays_to_its_end():
@@ -52,9 +56,9 @@ def test_baseline_config0_replays_to_its_end():
     the reference is decided by the rounding of a singular SuperLU pivot (floating pockets) are counted, not hidden."""
     fx = Fixture('d14_dc_nothing_1000')
     assert len(fx.actions) == 1000 and str(fx.config['loadflow_mode']).upper() == 'DC'
-    n_bad = int(fx.mismatch.sum())
+    n_bad = int((fx.mismatch != 0).sum())
     # both sides end the game on each of those steps; only the flag differs (loads cut vs diverging)
-    assert n_bad <= 3 and np.all(fx.done[fx.mismatch])
+    assert n_bad <= 3 and np.all(fx.done[fx.mismatch != 0])
     assert int(fx.done.sum()) == 139
 
 
