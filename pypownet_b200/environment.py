@@ -388,10 +388,49 @@ class RunEnv(object):
         self.observation_space = ObservationSpace(case.n_gen, case.n_load, case.n_line, case.n_sub,
                                                   self.game.n_timesteps_horizon_maintenance)
         self.reward_signal = self._vec.parameters.get_reward_signal_class()()
-        self._custom_reward = not hasattr(self.reward_signal, 'too_many_productions_cut')
+        self._custom_reward = not self._is_shipped_reward(self.reward_signal)
         self.last_rewards = []
         self._last_obs = self._vec.obs[0].cpu().numpy().copy()
         return self.get_observation(True)
+
+    @staticmethod
+    def _is_shipped_reward(sig):
+        """True when the plug-in is the shipped five-term reward WITH the shipped constants (parameters/default14/
+        reward_signal.py:11-43: every factor is a fixed multiple of `constant`): only then does the step kernel's reward
+        equal the plug-in's.  A plug-in that keeps the attribute names but tunes a factor is evaluated on the host."""
+        k = getattr(sig, 'too_many_productions_cut', None)
+        if k is None:
+            return False
+        c = -float(k)
+        expect = {'multiplicative_factor_line_usage_reward': -1., 'multiplicative_factor_distance_initial_grid': -.02,
+                  'multiplicative_factor_number_loads_cut': -c / 5., 'multiplicative_factor_number_prods_cut': -c / 10.,
+                  'connexity_exception_reward': -c, 'loadflow_exception_reward': -c,
+                  'multiplicative_factor_number_illegal_broken_line_switch': -c / 100.,
+                  'multiplicative_factor_number_illegal_oncooldown_line_switch': -c / 100.,
+                  'multiplicative_factor_number_illegal_oncooldown_substation_switch': -c / 100.,
+                  'multiplicative_factor_number_illegal_lines_reconnection': -c / 100.,
+                  'too_many_consumptions_cut': -c, 'too_much_activated_elements': -5 * c,
+                  'multiplicative_factor_number_line_switches': -.2, 'multiplicative_factor_number_node_switches': -.1}
+        for name, value in expect.items():
+            if hasattr(sig, name) and float(getattr(sig, name)) != value:
+                return False
+        return True
+
+    def _corrected_action(self, action, illegal_row):
+        """The action as the reference leaves it after an IllegalActionException (game.py:809-854 mutates the submitted
+        action in place): everything dropped when too many elements were activated, else the illegal line switches and
+        the switches of substations on cooldown zeroed."""
+        c = self._vec.case
+        N, S = c.n_line, c.n_sub
+        a = np.array(action.as_array(), dtype=np.int64)
+        nt = c.n_gen + c.n_load + 2 * N
+        if illegal_row[0]:
+            a[:] = 0
+        else:
+            bad_lines = illegal_row[1:1 + N].astype(bool) | illegal_row[1 + N:1 + 2 * N].astype(bool)
+            a[nt:][bad_lines] = 0
+            a[:nt][illegal_row[1 + 2 * N:].astype(bool)[np.asarray(c.elem_sub)]] = 0
+        return self.action_space.array_to_action(a)
 
     def get_observation(self, as_array=True):
         return self._last_obs.copy() if as_array else self.observation_space.array_to_observation(self._last_obs)
@@ -421,6 +460,8 @@ class RunEnv(object):
         flag = self._flag_object(code, illegal_row)
         observation = None if done else self.observation_space.array_to_observation(obs_row)
         if self._custom_reward:                      # user plug-in: evaluated on the host, as the reference does
+            if code == _lib.FLAG_ILLEGAL_ACTION or illegal_row.any():
+                action = self._corrected_action(action, illegal_row)
             reward_aslist = self.reward_signal.compute_reward(observation=observation, action=action, flag=flag)
         else:                                        # the shipped five-term reward is computed by the step kernel
             reward_aslist = [float(v) for v in reward_row]
@@ -442,7 +483,7 @@ class RunEnv(object):
         to_simulate = self.action_space._verify_action_shape(action)
         a = to_simulate.as_array().astype(np.uint8)[None]
         obs, reward, done, flag = self._vec.simulate(a)
-        ill = np.zeros(1 + 2 * self._vec.case.n_line + self._vec.case.n_sub, dtype=np.uint8)
+        ill = self._vec.sim_illegal[0].cpu().numpy()
         return self._finish(obs[0].cpu().numpy(), reward[0].cpu().numpy(), bool(done[0].item()),
                             int(flag[0].item()), ill, to_simulate, do_sum)
 

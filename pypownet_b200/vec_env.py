@@ -38,7 +38,15 @@ class VecRunEnv(object):
         self.device = torch.device('cuda', device)
         self.device_index = device
         if thermal_limits is None:
-            thermal_limits = self.chronics[0].imaps          # the first chronic's limits (game.py:301-304)
+            # the limits of the chronic an env STARTS on, never refreshed (game.py:301-304); one set per handle: envs
+            # that start on different chronics must agree (the shipped chronics of an environment all do)
+            starts = [0] if start_chronics is None else sorted(set(int(c) for c in np.asarray(start_chronics).ravel()))
+            thermal_limits = self.chronics[starts[0]].imaps
+            for c in starts[1:]:
+                if not np.array_equal(np.asarray(self.chronics[c].imaps), np.asarray(thermal_limits)):
+                    raise ValueError('the envs of one handle start on chronics with different thermal limits '
+                                     '(%s, %s): pass thermal_limits explicitly' % (self.chronics[starts[0]].name,
+                                                                                   self.chronics[c].name))
         self.thermal_limits = np.asarray(thermal_limits, dtype=np.float64)
         if reward_constant is None:
             reward_constant = float(case.n_sub)
@@ -79,7 +87,9 @@ class VecRunEnv(object):
         const = getattr(par.get_reward_signal_class()(), 'too_many_productions_cut', None) \
             if par.get_reward_signal_class() is not None else None
         kw.setdefault('reward_constant', -const if const is not None else float(case.n_sub))
-        kw.setdefault('start_chronics', np.full(n_envs, start_id % len(chron), dtype=np.int32))
+        if not 0 <= int(start_id) < len(chron):          # the reference indexes its chronic list with start_id
+            raise IndexError('start_id %d out of range: %d chronics in %s' % (start_id, len(chron), par.get_chronics_path()))
+        kw.setdefault('start_chronics', np.full(n_envs, int(start_id), dtype=np.int32))
         env = cls(case, par.simulator_configuration, chron.chronics, n_envs, game_over_mode=game_over_mode,
                   without_overflow_cutoff=without_overflow_cutoff, loop_mode=chronic_looping_mode, **kw)
         env.parameters = par
@@ -169,9 +179,11 @@ class VecRunEnv(object):
         reward = torch.zeros((rows, 5), dtype=torch.float64, device=dev)
         done = torch.zeros((rows,), dtype=torch.uint8, device=dev)
         flag = torch.zeros((rows,), dtype=torch.int32, device=dev)
+        # illegality masks of the simulated actions (has_too_much_activations | reconnections | line cooldowns | substations)
+        self.sim_illegal = torch.zeros((rows, 1 + 2 * self.case.n_line + self.case.n_sub), dtype=torch.uint8, device=dev)
         with torch.cuda.device(self.device):
             self._check(self.lib.ppn_simulate(self.handle, n_candidates, _ptr(a), _ptr(obs), self.obs_length,
-                                              _ptr(reward), _ptr(done), _ptr(flag), None, self._stream()))
+                                              _ptr(reward), _ptr(done), _ptr(flag), _ptr(self.sim_illegal), self._stream()))
         return obs, reward, done, flag
 
     def process_game_over(self, mask=None):

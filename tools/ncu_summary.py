@@ -1,5 +1,5 @@
 """Summarises gpurun_out/prof_<tag>.ncu-rep and launches_<tag>.csv into profiles/ (text + traffic.json).
-    python tools/ncu_summary.py <tag> <grid> <envs>"""
+    python tools/ncu_summary.py <tag> <grid> <envs> [agent]"""
 import csv
 import json
 import os
@@ -8,6 +8,7 @@ import sys
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 tag, grid, envs = sys.argv[1], sys.argv[2], int(sys.argv[3])
+agent = sys.argv[4] if len(sys.argv) > 4 else 'nothing'
 rep = os.path.join(ROOT, 'gpurun_out', 'prof_%s.ncu-rep' % tag)
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
@@ -28,6 +29,13 @@ for r in rows[2:]:
     for w in want:
         if w in hdr:
             out.append('  %-70s %s %s' % (w, r[hdr.index(w)], units[hdr.index(w)]))
+    for i, h in enumerate(hdr):   # local memory (register spills / stack): instructions and bytes
+        if '_local' in h and h.endswith('.sum'):
+            try:
+                if float(r[i].replace(',', '')) > 0:
+                    out.append('  %-70s %s %s' % (h, r[i], units[i]))
+            except ValueError:
+                pass
     for i, h in enumerate(hdr):
         if 'warp_issue_stalled' in h and h.endswith('_per_warp_active.pct'):
             try:
@@ -62,7 +70,10 @@ with open(os.path.join(ROOT, 'profiles', '%s_ncu_summary.txt' % tag), 'w') as f:
     f.write('\n'.join(out) + '\n')
 tp = os.path.join(ROOT, 'profiles', 'traffic.json')
 t = json.load(open(tp)) if os.path.exists(tp) else {}
-t['%s_%d' % (grid, envs)] = sum(traffic) / len(traffic)
-t['_source'] = 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, tag %s' % tag
+t['%s_%d%s' % (grid, envs, '' if agent == 'nothing' else '_' + agent)] = sum(traffic) / len(traffic)
+t.setdefault('_source', {})
+if not isinstance(t['_source'], dict):
+    t['_source'] = {}
+t['_source']['%s_%d%s' % (grid, envs, '' if agent == 'nothing' else '_' + agent)] = 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none, tag %s' % tag
 json.dump(t, open(tp, 'w'), indent=1)
 print('\n'.join(out))

@@ -4,11 +4,13 @@ import ctypes, os, subprocess, sys
 import numpy as np, torch
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 sys.path.insert(0, ROOT)
-lib_dbg = os.path.join(ROOT, 'gpurun_out', 'libpypownet_b200_timing.so')
+lib_dbg = os.path.join(ROOT, 'build', 'libpypownet_b200_timing.so')   # build it in the container: it travels with the snapshot
 import __graft_entry__ as g
-if not os.path.exists(lib_dbg):
+if not os.path.exists(lib_dbg) or '--build' in sys.argv:
     os.makedirs(os.path.dirname(lib_dbg), exist_ok=True)
     subprocess.run(['/usr/local/cuda/bin/nvcc'] + g.NVCC_FLAGS + ['-DPPN_TIMING', '-o', lib_dbg] + [os.path.join(g.CSRC, s) for s in g.SOURCES], check=True)
+if '--build' in sys.argv:
+    sys.exit(0)
 from pypownet_b200 import _lib
 _lib.LIB_PATH = lib_dbg
 import bench
@@ -16,7 +18,7 @@ from pypownet_b200.vec_env import VecRunEnv
 grid = sys.argv[1] if len(sys.argv) > 1 else 'case14'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 case, cfg, chronics, imaps = bench.build_workload(grid)
-sc, sr = bench.env_starts(B)
+sc, sr = bench.shard_starts(B, 0, 1)
 env = VecRunEnv(case, cfg, chronics, B, reward_constant=float(case.n_sub), thermal_limits=imaps, start_chronics=sc, start_rows=sr)
 lib = env.lib
 lib.ppn_debug_timing.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
