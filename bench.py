@@ -428,6 +428,18 @@ def measure(ctx, grid, envs, agent, cascade, steps, warmup, with_e2e=True, sampl
         out['e2e'] = {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h}
         out['per_rank_e2e_ms_per_step'] = [round(1e3 * r[0] / steps, 4) for r in e2e_all]
         out['per_rank_e2e_d2h_gbs'] = [round(d2h * steps / r[0] / 1e9, 2) for r in e2e_all]
+        # the same loop with float32 observation rows (ppn_step_host_f32: an extension, NOT the headline -- the
+        # reference's observation is float64)
+        for _ in range(3):
+            env.step_pinned(act_pinned, obs_dtype=torch.float32)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            env.step_pinned(host_bank[k % 16] if host_bank is not None else act_pinned, obs_dtype=torch.float32)
+        torch.cuda.synchronize()
+        f32_all = ctx.gather_list([time.perf_counter() - t0])
+        out['e2e_f32'] = {'value': world * B * steps / max(r[0] for r in f32_all), 'unit': 'env-steps/s',
+                          'd2h_bytes_per_step': B * (case.obs_dynamic_length * 4 + 5 * 8 + 1 + 4)}
     if pg is not None:
         pg.close()
     env.close()
@@ -461,7 +473,8 @@ def run_b200(args):
             r = measure(ctx, grid, envs, agent, cascade, k, 3, with_e2e=True, sharding_mode=args.sharding)
             secondary.append({'workload': name, 'grid': grid, 'envs_per_gpu': envs, 'n_gpus': world, 'steps': k,
                               'value': r['value'], 'unit': 'env-steps/s', 'ms_per_step': r['ms_per_step'],
-                              'e2e': r['e2e']['value'], 'roofline_frac': r['roofline']['frac'],
+                              'e2e': r['e2e']['value'], 'e2e_float32_observations': r['e2e_f32']['value'],
+                              'roofline_frac': r['roofline']['frac'],
                               'algorithmic_bytes_per_env_step': r['algorithmic_bytes_per_env_step'],
                               'gpu_launches': r['launches'], 'per_rank_ms_per_step': r['per_rank_ms_per_step'],
                               'counters': r['counters']})
@@ -488,7 +501,8 @@ def run_b200(args):
                   'step kernels store their reward/done/flag rows into rank 0\'s GPU memory over NVLink (peer mapping); '
                   'rank 0 copies them to the host one step behind on a side stream; NCCL only for set-up and timing',
                   'per_rank_ms_per_step': m['per_rank_ms_per_step'],
-                  'per_rank_e2e_d2h_gbs': m['per_rank_e2e_d2h_gbs']})
+                  'per_rank_e2e_d2h_gbs': m['per_rank_e2e_d2h_gbs'],
+                  'e2e_float32_observations': m['e2e_f32']})
     line = {'metric': 'env steps/sec (batched grids)', 'value': m['value'], 'unit': 'env-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': m['ms_per_step'],
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',

@@ -196,6 +196,12 @@ int ppn_peer_read(int device, void* host_dst, const void* dev_src, uint64_t byte
 int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_host, int64_t obs_stride, double* reward_host,
                   uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset);
 
+/* ppn_step_host with float32 observation rows (obs_stride counts floats): half the bytes over PCIe -- each value is the
+ * float64 one rounded once.  An extension for host-side agents that feed a float32 network; the reference's as_array is
+ * float64 and ppn_step_host stays the drop-in.  Every result buffer must be page-locked. */
+int ppn_step_host_f32(ppn_env* env, const uint8_t* act_host, float* obs_host, int64_t obs_stride, double* reward_host,
+                      uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset);
+
 int ppn_state_width(const ppn_env* env, int field);   /* elements per env of a PPN_STATE_* field */
 int ppn_get_state(ppn_env* env, int field, void* out_dev, void* stream);
 int ppn_set_state(ppn_env* env, int field, const void* in_dev, void* stream);

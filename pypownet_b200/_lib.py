@@ -76,6 +76,7 @@ SYMBOLS = {
     'ppn_process_game_over': (C.c_int, [VP, VP, VP, C.c_int64, VP]),
     'ppn_action_valid': (C.c_int, [VP, VP, VP, VP]),
     'ppn_step_host': (C.c_int, [VP, VP, VP, C.c_int64, VP, VP, VP, VP, C.c_int]),
+    'ppn_step_host_f32': (C.c_int, [VP, VP, VP, C.c_int64, VP, VP, VP, VP, C.c_int]),
     'ppn_set_result_pack': (C.c_int, [VP, VP]),
     'ppn_set_env_trace': (C.c_int, [VP, VP]),
     'ppn_sparse_selfcheck': (C.c_int, [C.c_int, C.c_int, VP, VP, C.c_int, C.c_uint32, VP, VP]),

@@ -622,6 +622,13 @@ static int create_body(const ppn_case* g, const ppn_config* cfg, int n_envs, int
     auto plan = [&](int mode) {
         int want = n1 * (n1 | 1) + n2 * (n2 | 1);
         if (mode == 1) want = (n1 + 1) * (n1 | 1) + (n2 + 1) * (n2 | 1) + env->sp_need[0] + env->sp_blob_dbl[0];
+        if (mode == 1 && tpe <= 32 && !getenv("PPN_WARP_TABLES_SMEM")) {
+            // warp per env: the inverses and the factor values live in shared memory, the read-only index tables are read
+            // through L1 from their one copy in HBM (every env staging its own copy cost a third of the shared memory:
+            // IEEE-30 went from 6 to 8 resident envs per SM), and the dense top blocks of the hybrid solver are not used
+            const PpnDevSparse& u = env->dc.sp[0];
+            want = (n1 + 1) * (n1 | 1) + (n2 + 1) * (n2 | 1) + 2 * ppn_sp_factor_doubles(u.n, u.nnz);
+        }
         if (mode >= 2) want = env->sp_need[0] + env->sp_blob_dbl[0];
         if (cfg->pf_alg == 1 && tpe <= 32) {   // Newton-Raphson: the Jacobian of the un-split grid + right-hand side
             const int nj = n1 + n2;
@@ -771,7 +778,7 @@ static int launch(ppn_env* env, PpnStepArgs& a, cudaStream_t s) {
     if (a.n_envs <= 0) { a.n_envs = env->B; a.env_off = 0; }   // whole batch unless the caller set a chunk
     {   // observation rows as TMA bulk stores when every row starts on a 16-byte boundary
         static const int no_bulk = getenv("PPN_NO_BULK") != nullptr;
-        a.obs_bulk = !no_bulk && a.obs && (reinterpret_cast<size_t>(a.obs) & 15) == 0 && (a.obs_stride & 1) == 0;
+        a.obs_bulk = !no_bulk && a.obs && (reinterpret_cast<size_t>(a.obs) & 15) == 0 && (a.obs_stride & (a.obs_f32 ? 3 : 1)) == 0;
     }
     if (a.n_cand <= 0) a.n_cand = 1;
     if (a.mode == PPN_MODE_SIMULATE && a.n_cand > 1) {
@@ -950,8 +957,25 @@ static bool is_pinned(const void* p) {
 // RunEnv.step with HOST buffers.  The batch is cut into chunks; chunk i runs  actions H2D -> step kernel -> results D2H
 // on its own stream, so the copies of the chunks that finished overlap the kernels of those still running.  Page-locked
 // caller buffers are used in place; pageable ones go through the handle's pinned staging buffers.
+static int step_host_impl(ppn_env* env, const uint8_t* act_host, double* obs_host, int64_t obs_stride, double* reward_host,
+                          uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset, bool f32);
+
 extern "C" int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_host, int64_t obs_stride, double* reward_host,
                              uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset) {
+    return step_host_impl(env, act_host, obs_host, obs_stride, reward_host, done_host, flag_host, illegal_host, auto_reset, false);
+}
+
+// Same call with the observation rows delivered as float32 (obs_stride counts floats): half the bytes over PCIe.  Every
+// value is the float64 one rounded once (the reference's Observation.as_array is float64; agents that feed a float32
+// network convert anyway).  Page-locked result buffers only: the rows are written by the kernel itself.
+extern "C" int ppn_step_host_f32(ppn_env* env, const uint8_t* act_host, float* obs_host, int64_t obs_stride, double* reward_host,
+                                 uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset) {
+    return step_host_impl(env, act_host, reinterpret_cast<double*>(obs_host), obs_stride, reward_host, done_host, flag_host,
+                          illegal_host, auto_reset, true);
+}
+
+static int step_host_impl(ppn_env* env, const uint8_t* act_host, double* obs_host, int64_t obs_stride, double* reward_host,
+                          uint8_t* done_host, int32_t* flag_host, uint8_t* illegal_host, int auto_reset, bool f32) {
     int rc = check_ready(env, "ppn_step_host");
     if (rc) return rc;
     if (obs_host && obs_stride < env->OBSD) return fail(env, PPN_E_INVALID, "ppn_step_host: obs_stride smaller than the dynamic observation");
@@ -980,7 +1004,7 @@ extern "C" int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_
             }
             PpnStepArgs a{};
             a.mode = PPN_MODE_STEP; a.auto_reset = auto_reset; a.act = act_host ? env->d_act : nullptr;
-            a.obs = (double*)dev[0]; a.obs_stride = obs_stride; a.reward = (double*)dev[1]; a.done = (uint8_t*)dev[2];
+            a.obs = (double*)dev[0]; a.obs_stride = obs_stride; a.obs_f32 = f32 ? 1 : 0; a.reward = (double*)dev[1]; a.done = (uint8_t*)dev[2];
             a.flag = (int32_t*)dev[3]; a.illegal = (uint8_t*)dev[4];
             rc = launch(env, a, s);
             if (rc) return rc;
@@ -989,6 +1013,7 @@ extern "C" int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_
             return PPN_OK;
         }
     }
+    if (f32) return fail(env, PPN_E_UNSUPPORTED, "ppn_step_host_f32: every result buffer must be page-locked (cudaHostRegister / pin_memory)");
     // ---- staged / chunked copies.  Rows of envs that ended without auto-reset hold no observation and must stay
     // untouched, which a plain copy cannot do: those go through the staging buffer.
     const bool obs_direct = obs_host && auto_reset && is_pinned(obs_host);

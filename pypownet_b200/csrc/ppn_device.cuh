@@ -149,6 +149,7 @@ struct PpnStepArgs {
     double* obs;                // [rows][obs_stride] or NULL
     long long obs_stride;
     int obs_bulk;               // 1: rows leave through one TMA bulk store each (16-byte aligned rows)
+    int obs_f32;                // 1: `obs` holds float rows (obs_stride counts floats): ppn_step_host_f32
     double* reward;             // [rows][5] or NULL
     uint8_t* done;              // [rows] or NULL
     int32_t* flag;              // [rows] or NULL

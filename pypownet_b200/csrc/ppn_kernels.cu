@@ -234,29 +234,30 @@ __device__ __forceinline__ void sts64(unsigned a, double v) {
 // rank-1 update runs on registers.  `i` = row of this lane, `nsteps` is uniform over `syncmask` (max n of the
 // matrices inverted side by side), `piv_s` = NR doubles per matrix.  Same operation order as gj_invert.
 // NR = 16: pivot steps fully unrolled (static register indices, no select chains); two matrices fit one warp.
-__device__ __noinline__ void gj16_rows_in_registers(unsigned m_s, int n, int ld, int i, int nsteps, unsigned piv_s,
-                                                    unsigned syncmask) {
-    double row[16];
+template <int NR>
+__device__ __forceinline__ void gj_rows_in_registers_impl(unsigned m_s, int n, int ld, int i, int nsteps, unsigned piv_s,
+                                                          unsigned syncmask) {
+    double row[NR];
     const bool mine = i < n;
 #pragma unroll
-    for (int j = 0; j < 16; j++) row[j] = (mine && j < n) ? lds64(m_s + 8u * (unsigned)(i * ld + j)) : 0.0;
+    for (int j = 0; j < NR; j++) row[j] = (mine && j < n) ? lds64(m_s + 8u * (unsigned)(i * ld + j)) : 0.0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
+    for (int k = 0; k < NR; k++) {
         if (k < nsteps) {
             if (mine && i == k) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) sts64(piv_s + 8u * j, row[j]);
+                for (int j = 0; j < NR; j++) sts64(piv_s + 8u * j, row[j]);
             }
             __syncwarp(syncmask);
             if (mine && k < n) {
                 const double p = 1.0 / lds64(piv_s + 8u * k);
                 if (i == k) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) row[j] = (j == k) ? p : row[j] * p;
+                    for (int j = 0; j < NR; j++) row[j] = (j == k) ? p : row[j] * p;
                 } else {
                     const double ci = row[k] * p;
 #pragma unroll
-                    for (int j = 0; j < 16; j++)
+                    for (int j = 0; j < NR; j++)
                         if (j != k) row[j] = fma(-ci, lds64(piv_s + 8u * j), row[j]);
                     row[k] = -ci;
                 }
@@ -266,10 +267,20 @@ __device__ __noinline__ void gj16_rows_in_registers(unsigned m_s, int n, int ld,
     }
     if (mine) {
 #pragma unroll
-        for (int j = 0; j < 16; j++)
+        for (int j = 0; j < NR; j++)
             if (j < n) sts64(m_s + 8u * (unsigned)(i * ld + j), row[j]);
     }
     __syncwarp(syncmask);
+}
+
+__device__ __noinline__ void gj16_rows_in_registers(unsigned m_s, int n, int ld, int i, int nsteps, unsigned piv_s,
+                                                    unsigned syncmask) {
+    gj_rows_in_registers_impl<16>(m_s, n, ld, i, nsteps, piv_s, syncmask);
+}
+
+// NR = 24: the dense top block of the hybrid solver (IEEE-118: 17 rows), one warp per matrix, a row per lane
+__device__ __noinline__ void gj24_rows_in_registers(unsigned m_s, int n, int ld, int i, unsigned piv_s) {
+    gj_rows_in_registers_impl<24>(m_s, n, ld, i, n, piv_s, PPN_FULL);
 }
 
 // ------------------------------------------------------------------------------------- sparse LDL^T (static pattern)
@@ -520,6 +531,13 @@ template <int TPE> __device__ __noinline__ void hyb_factor2(const PpnDevSparse& 
 // barrier.  `buf`: 4 * nt doubles of scratch.  No pivoting (the Schur complement of a positive definite matrix is
 // positive definite); a singular block yields inf/NaN -> "diverging".
 template <int TPE> __device__ __noinline__ void hyb_invert2(double* Z1, double* Z2, int nt, int ldz, double* buf, int tid) {
+    if (nt <= 24) {
+        // small blocks: one WARP per matrix with a row per lane in registers (pivot row through a 24-double shared buffer,
+        // __syncwarp only) -- no CTA barrier per pivot; measured on IEEE-118 (17 rows): 29 k cycles with the tiled version
+        if (tid < 64) gj24_rows_in_registers(saddr(tid < 32 ? Z1 : Z2), nt, ldz, tid & 31, saddr(buf) + (tid < 32 ? 0u : 8u * 24u));
+        __syncthreads();
+        return;
+    }
     constexpr int T = 5;
     const bool work = tid < 128, second = tid >= 64;
     const int ht = tid & 63, ti = ht >> 3, tj = ht & 7;
@@ -592,8 +610,12 @@ template <int TPE> __device__ __noinline__ void hyb_invert2(double* Z1, double* 
     __syncthreads();
 }
 
-// (B)^-1 w in place with the hybrid factor.  dg: reciprocal pivots below the cut.  Four lanes share a row in every step
-// (the hub rows of a grid are long) and combine with two shuffles: fixed order, deterministic.
+// (B)^-1 w in place with the hybrid factor.  dg: reciprocal pivots below the cut.
+// The sparse levels below the cut are tiny (IEEE-118: 25, 11, 6, 6 and 5 rows with at most 8 entries each going up, 48
+// rows of level 0 coming down): ONE warp walks them, a row per lane, with nothing but __syncwarp between levels, while
+// the other warps wait at a single barrier -- measured against the former all-threads version (four lanes per row, a
+// CTA barrier per level: 14 barriers and ~9 k cycles per solve).  The dense top block (gather, 17 x 17 product) stays
+// spread over the CTA, four lanes per row combined with two shuffles: fixed order, deterministic.
 template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp, unsigned tb, unsigned a_Lv, unsigned a_dg, const double* Z,
                                                              int ldz, unsigned a_w, int tid) {
     const unsigned a_lev = tb + 4u * sp.o_lev_rows_ptr, a_rowpk = tb + 4u * sp.o_rowpk, a_colpk = tb + 4u * sp.o_colpk,
@@ -601,32 +623,36 @@ template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp
     const int r0 = sp.cut_row, nt = sp.nt;
     const int t = tid >> 2, part = tid & 3;
     const int wrow = (tid >> 5) << 3;   // first row of a pass that falls to this warp (eight rows per warp)
-    constexpr int RS = TPE / 4;   // rows per pass
-    int s0 = lds32(a_lev + 4u);
-    for (int lv = 1; lv < sp.cut_lev; lv++) {   // sparse forward steps (rows of level 0 depend on nothing)
-        const int s1 = lds32(a_lev + 4u * (lv + 1));
+    if (tid < 32) {   // sparse forward steps (rows of level 0 depend on nothing)
+        int s0 = lds32(a_lev + 4u);
+        for (int lv = 1; lv < sp.cut_lev; lv++) {
+            const int s1 = lds32(a_lev + 4u * (lv + 1));
 #pragma unroll 1
-        for (int ib = s0; ib < s1; ib += RS) {
-            if (ib + wrow >= s1) break;   // no row of this pass falls to this warp (warp-uniform)
-            const int i = ib + t;
-            double y = 0.0;
-            if (i < s1) {
+            for (int i = s0 + tid; i < s1; i += 32) {
                 const unsigned pk = (unsigned)lds32(a_rowpk + 4u * i);
-                const int cnt = (int)(pk & 255u);
-                const unsigned ra = a_rpack + 4u * (pk >> 8);
+                const unsigned wi = a_w + 8u * i;
+                double acc = lds64(wi);
+                unsigned ra = a_rpack + 4u * (pk >> 8);
+                int cnt = (int)(pk & 255u);
 #pragma unroll 1
-                for (int q = part; q < cnt; q += 4) {
-                    const unsigned p0 = (unsigned)lds32(ra + 4u * q);
-                    y = fma(-lds64(a_Lv + (p0 >> 16)), lds64(a_w + (p0 & 0xffffu)), y);
+                for (; cnt >= 2; cnt -= 2, ra += 8u) {   // two entries per trip, loads first
+                    const unsigned p0 = (unsigned)lds32(ra), p1 = (unsigned)lds32(ra + 4u);
+                    const double l0 = lds64(a_Lv + (p0 >> 16)), x0 = lds64(a_w + (p0 & 0xffffu));
+                    const double l1 = lds64(a_Lv + (p1 >> 16)), x1 = lds64(a_w + (p1 & 0xffffu));
+                    acc = fma(-l0, x0, acc);
+                    acc = fma(-l1, x1, acc);
                 }
+                if (cnt) {
+                    const unsigned p0 = (unsigned)lds32(ra);
+                    acc = fma(-lds64(a_Lv + (p0 >> 16)), lds64(a_w + (p0 & 0xffffu)), acc);
+                }
+                sts64(wi, acc);
             }
-            y += __shfl_xor_sync(PPN_FULL, y, 1);
-            y += __shfl_xor_sync(PPN_FULL, y, 2);
-            if (i < s1 && part == 0) sts64(a_w + 8u * i, lds64(a_w + 8u * i) + y);
+            __syncwarp();
+            s0 = s1;
         }
-        __syncthreads();
-        s0 = s1;
     }
+    __syncthreads();
     // top block: y2 = w2 - L21 y1 (entries below the cut only)
     if (wrow < nt) {
         double y = 0.0;
@@ -669,29 +695,33 @@ template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp
         if (t < nt && part == 0) sts64(a_w + 8u * (r0 + t), x);
     }
     __syncthreads();
-    int e1 = r0;
-    for (int lv = sp.cut_lev - 1; lv >= 0; lv--) {   // sparse backward steps
-        const int e0 = lds32(a_lev + 4u * lv);
+    if (tid < 32) {   // sparse backward steps, down to level 0
+        int e1 = r0;
+        for (int lv = sp.cut_lev - 1; lv >= 0; lv--) {
+            const int e0 = lds32(a_lev + 4u * lv);
 #pragma unroll 1
-        for (int ib = e0; ib < e1; ib += RS) {
-            if (ib + wrow >= e1) break;
-            const int i = ib + t;
-            double y = 0.0;
-            if (i < e1) {
+            for (int i = e0 + tid; i < e1; i += 32) {
                 const unsigned pk = (unsigned)lds32(a_colpk + 4u * i);
-                const int cnt = (int)(pk & 255u);
-                const unsigned en0 = pk >> 8;
+                const unsigned wi = a_w + 8u * i;
+                double acc = lds64(wi) * lds64(a_dg + 8u * i);
+                unsigned en = pk >> 8;
+                int cnt = (int)(pk & 255u);
 #pragma unroll 1
-                for (int q = part; q < cnt; q += 4)
-                    y = fma(-lds64(a_Lv + 8u * (en0 + q)), lds64(a_w + lds16(a_rowoff + 2u * (en0 + q))), y);
+                for (; cnt >= 2; cnt -= 2, en += 2u) {
+                    const int q0 = lds16(a_rowoff + 2u * en), q1 = lds16(a_rowoff + 2u * en + 2u);
+                    const double l0 = lds64(a_Lv + 8u * en), l1 = lds64(a_Lv + 8u * en + 8u);
+                    const double x0 = lds64(a_w + q0), x1 = lds64(a_w + q1);
+                    acc = fma(-l0, x0, acc);
+                    acc = fma(-l1, x1, acc);
+                }
+                if (cnt) acc = fma(-lds64(a_Lv + 8u * en), lds64(a_w + lds16(a_rowoff + 2u * en)), acc);
+                sts64(wi, acc);
             }
-            y += __shfl_xor_sync(PPN_FULL, y, 1);
-            y += __shfl_xor_sync(PPN_FULL, y, 2);
-            if (i < e1 && part == 0) sts64(a_w + 8u * i, fma(lds64(a_w + 8u * i), lds64(a_dg + 8u * i), y));
+            __syncwarp();
+            e1 = e0;
         }
-        __syncthreads();
-        e1 = e0;
     }
+    __syncthreads();
 }
 
 // L D L^T x = w in place; dg holds the RECIPROCAL pivots.  The rows of a level are contiguous (the host sorts the
@@ -1209,6 +1239,10 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
     // the rectangular voltages (read by neighbours) and the mismatch vectors (read by the solves) go through
     // shared memory.
     constexpr int RB = D::NB_MAX > 0 ? (D::NB_MAX + TPE - 1) / TPE : (TPE == 256 ? 1 : 2);   // <= 256 buses (CTA), <= 64 (warp)
+    // CTA-per-env kernels (two buses per thread, 168 registers, out-of-line solver calls) keep the loop-invariant part of
+    // that state -- injections, Ybus diagonal -- in shared memory and recompute the bus powers for pfsoln: fewer live
+    // registers across the solver calls, i.e. less local-memory traffic (ncu: 27 KB of spill write-backs per env-step)
+    constexpr bool LEAN = TPE > 32;
     double r_vm[RB], r_rvm[RB], r_va[RB], r_cs[RB], r_sn[RB], r_pin[RB], r_qin[RB], r_ydr[RB], r_ydi[RB], r_sr[RB], r_si[RB];
     int r_t[RB], r_ip[RB], r_iq[RB], r_deg[RB], r_k0[RB], r_step[RB];
     // solve mode: the mismatch vectors are indexed by factor row (zero on the identity rows) and are solved in place
@@ -1241,7 +1275,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         r_rvm[r] = 1.0 / vm;
         r_va[r] = atan2(vi, vr);           // radians
         r_cs[r] = vr / vm; r_sn[r] = vi / vm;
-        r_pin[r] = e.pin()[b]; r_qin[r] = e.qin()[b];
+        if (!LEAN) { r_pin[r] = e.pin()[b]; r_qin[r] = e.qin()[b]; }
         r_ip[r] = t != PPN_BT_REF ? (solve_mode ? (int)sp->bus_row[b] : (int)e.idxp()[b]) : 0;
         r_iq[r] = t == PPN_BT_PQ ? (solve_mode ? (int)sp->bus_row[b] : (int)e.idxq()[b]) : 0;
         r_deg[r] = e.deg()[b];
@@ -1322,7 +1356,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                 if (ispq && to == PPN_BT_PQ) f2.Lv[pos] -= e.ey()[2 * k + 1];
             }
         }
-        r_ydr[r] = yr; r_ydi[r] = yi;
+        if (LEAN) { e.ydr()[b] = yr; e.ydi()[b] = yi; } else { r_ydr[r] = yr; r_ydi[r] = yi; }
         if (!sp) {
             if (inp) M1[i * ld1 + i] += d1;
             if (ispq) M2[iq * ld2 + iq] += -yi;
@@ -1420,7 +1454,8 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
             const int t = r_t[r];
             if (t != PPN_BT_PV && t != PPN_BT_PQ) continue;
             const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
-            double ir = r_ydr[r] * vr - r_ydi[r] * vi, ii = r_ydr[r] * vi + r_ydi[r] * vr;
+            const double ydr_ = LEAN ? e.ydr()[tid + r * TPE] : r_ydr[r], ydi_ = LEAN ? e.ydi()[tid + r * TPE] : r_ydi[r];
+            double ir = ydr_ * vr - ydi_ * vi, ii = ydr_ * vi + ydi_ * vr;
             double jr = 0.0, ji = 0.0;
             {   // even entries accumulate in (ir, ii), odd ones in (jr, ji): two independent chains, one 16-byte load
                 // per admittance and per neighbour voltage
@@ -1444,13 +1479,13 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
             }
             ir += jr; ii += ji;
             const double sr = vr * ir + vi * ii, si = vi * ir - vr * ii;   // V conj(I)
-            r_sr[r] = sr; r_si[r] = si;
+            if (!LEAN) { r_sr[r] = sr; r_si[r] = si; }
             const double rvm = r_rvm[r];   // 1/Vm only changes in the Q half-iterations
-            const double pm = (sr - r_pin[r]) * rvm;
+            const double pm = (sr - (LEAN ? e.pin()[tid + r * TPE] : r_pin[r])) * rvm;
             e.P()[r_ip[r]] = pm;
             open |= !(fabs(pm) < cfg.tol);
             if (t == PPN_BT_PQ) {
-                const double qm = (si - r_qin[r]) * rvm;
+                const double qm = (si - (LEAN ? e.qin()[tid + r * TPE] : r_qin[r])) * rvm;
                 e.Q()[r_iq[r]] = qm;
                 open |= !(fabs(qm) < cfg.tol);
             }
@@ -1468,12 +1503,12 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                 hyb_factor2<TPE>(*sp->d, sp->tb, SpsFactor{saddr(f1.T), saddr(f1.Lv), saddr(f1.dg)},
                                  SpsFactor{saddr(f2.T), saddr(f2.Lv), saddr(f2.dg)}, Z1, Z1 + sp->d->nt * ldz, ldz, tid);
                 PPN_TICK(8);
-                hyb_invert2<TPE>(Z1, Z1 + sp->d->nt * ldz, sp->d->nt, ldz, e.ydr(), tid);   // ydr | ydi: 2 NB doubles, the Ybus diagonal lives in registers here
+                hyb_invert2<TPE>(Z1, Z1 + sp->d->nt * ldz, sp->d->nt, ldz, e.cs(), tid);   // cs | sn: 2 NB doubles of scratch (the Ybus diagonal sits in ydr | ydi)
                 if (bd && (bd->k[0] | bd->k[1])) {
-                    // W = A^-1 B column by column (the solve works on a vector in shared memory: ydr is free here), then
+                    // W = A^-1 B column by column (the solve works on a vector in shared memory: cs | sn are free), then
                     // the Schur complements C - B^T W row by row (owner of the sister bus) and their inverses
                     const int nU = sp->n;
-                    double* col = e.ydr();
+                    double* col = e.cs();
                     for (int m = 0; m < 2; m++) {
                         const SpFactor& fm = m == 0 ? f1 : f2;
                         const double* Zm = Z1 + (m == 0 ? 0 : sp->d->nt * ldz);
@@ -1549,10 +1584,11 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
         const int s = b >= S ? b - S : b, node = b >= S ? 1 : 0;
         const int g = c.gen_of_sub[s];
         if (g >= 0 && e.gnode()[g] == node && e.gstat()[g] > 0) {
-            double sr = r_sr[r], si = r_si[r];
-            if (t == PPN_BT_REF) {   // the reference bus is not part of the mismatch vectors
+            double sr = LEAN ? 0.0 : r_sr[r], si = LEAN ? 0.0 : r_si[r];
+            if (t == PPN_BT_REF || LEAN) {   // the reference bus is not part of the mismatch vectors
                 const double vr = r_vm[r] * r_cs[r], vi = r_vm[r] * r_sn[r];
-                double ir = r_ydr[r] * vr - r_ydi[r] * vi, ii = r_ydr[r] * vi + r_ydi[r] * vr;
+                const double ydr_ = LEAN ? e.ydr()[b] : r_ydr[r], ydi_ = LEAN ? e.ydi()[b] : r_ydi[r];
+                double ir = ydr_ * vr - ydi_ * vi, ii = ydr_ * vi + ydi_ * vr;
                 for (int q = 0; q < r_deg[r]; q++) {
                     const int k = r_k0[r] + r_step[r] * q;
                     const int o = e.eoth()[k];
@@ -2104,14 +2140,16 @@ __device__ __forceinline__ void reset_grid(Env<TPE, D>& e, const PpnDevCase& c) 
 // assembled in shared memory (`stage`: the matrix area, free once the cascade is over) and leaves in one linear,
 // fully coalesced sweep -- `out` may be device memory or page-locked host memory written over PCIe (ppn_step_host).
 // stage == nullptr: the fields are written to `out` directly.
-template <int TPE, class D>
-__device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevChronics& ch, double* out,
-                                                  double* stage, bool bulk) {
+// T = double (the reference's dtype) or float (ppn_step_host_f32: half the bytes over PCIe for host-side agents that feed
+// a float32 network anyway; every value is the double one rounded once).
+template <int TPE, class D, class T>
+__device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevChronics& ch, T* out,
+                                                  T* stage, bool bulk) {
     const int G = e.G, L = e.L, N = e.N, S = e.S, tid = e.tid;
     compute_isolated(e);
     const float* row = chronic_row(ch, e.cursor()[0], max(e.cursor()[1], 0));   // maintenance horizon, date
     const float* prow = chronic_row(ch, e.misc()[6], e.misc()[7]);               // planned injections
-    double* o = stage ? stage : out;
+    T* o = stage ? stage : out;
     for (int l = tid; l < L; l += TPE) {
         o[l] = e.lpd()[l];
         o[L + l] = e.mark()[e.lbus()[l]] ? 1.0 : 0.0;
@@ -2164,7 +2202,7 @@ __device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCa
     }
     if (stage) {
         const int n = 7 * L + 7 * G + 13 * N + S + 6;
-        const int nb = n & ~1;                      // bulk copies move multiples of 16 bytes
+        const int nb = n & ~(int)(16 / sizeof(T) - 1);   // bulk copies move multiples of 16 bytes
         if (bulk && (reinterpret_cast<size_t>(out) & 15) == 0) {
             // one TMA bulk store per row (cp.async.bulk shared -> global): full-width write transactions, which is
             // what makes page-locked host memory behind PCIe a usable destination, and no store loop for the warp
@@ -2172,9 +2210,9 @@ __device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCa
             env_sync<TPE>(e.mask);
             if (tid == 0) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                             :: "l"(out), "r"(saddr(stage)), "r"(nb * 8) : "memory");
+                             :: "l"(out), "r"(saddr(stage)), "r"(nb * (int)sizeof(T)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                if (nb < n) out[nb] = stage[nb];
+                for (int i = nb; i < n; i++) out[i] = stage[i];
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the source may be reused / freed
             }
             env_sync<TPE>(e.mask);
@@ -2408,7 +2446,12 @@ ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, 
     // ---- outputs
     if (args.obs && !done) {
         flows_ampere(e, c);
-        write_observation(e, c, ch, args.obs + (size_t)slot * args.obs_stride, args.mat_cap >= c.OBSD ? e.mat() : nullptr, args.obs_bulk != 0);
+        if (args.obs_f32)
+            write_observation<TPE, D, float>(e, c, ch, reinterpret_cast<float*>(args.obs) + (size_t)slot * args.obs_stride,
+                                             args.mat_cap >= c.OBSD ? reinterpret_cast<float*>(e.mat()) : nullptr, args.obs_bulk != 0);
+        else
+            write_observation<TPE, D, double>(e, c, ch, args.obs + (size_t)slot * args.obs_stride,
+                                              args.mat_cap >= c.OBSD ? e.mat() : nullptr, args.obs_bulk != 0);
     }
     if (!is_sim) {
         env_sync<TPE>(mask);

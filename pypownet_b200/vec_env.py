@@ -224,24 +224,30 @@ class VecRunEnv(object):
                                            flag.ctypes.data_as(C.c_void_p), None, 1 if auto_reset else 0))
         return obs_out, reward, done, flag
 
-    def step_pinned(self, actions_pinned, auto_reset=True):
+    def step_pinned(self, actions_pinned, auto_reset=True, obs_dtype=torch.float64):
         """End-to-end step for a host-side agent through ppn_step_host: actions in pinned host memory (uint8
-        [B, action_length] tensor, None = do-nothing) -> GPU, step, dynamic observation / reward / done / flag back into
-        pinned host tensors (reused per call), chunked so that copies overlap the kernels.  Synchronous."""
-        if not hasattr(self, '_pin'):
+        [B, action_length] tensor, None = do-nothing) -> GPU, step, dynamic observation / reward / done / flag written by
+        the step kernel straight into pinned host tensors (reused per call).  Synchronous.  obs_dtype=torch.float32 asks
+        for float32 observation rows (ppn_step_host_f32: half the bytes over PCIe; the reference's dtype is float64)."""
+        if obs_dtype not in (torch.float64, torch.float32):
+            raise ValueError('obs_dtype must be torch.float64 or torch.float32')
+        key = '_pin64' if obs_dtype == torch.float64 else '_pin32'
+        if not hasattr(self, key):
             B = self.n_envs
-            stride = (self.obs_dynamic_length + 1) & ~1      # 16-byte aligned rows: one TMA bulk store per row
-            self._pin_obs_full = torch.empty((B, stride), dtype=torch.float64).pin_memory()
-            self._pin = (self._pin_obs_full[:, :self.obs_dynamic_length],
-                         torch.empty((B, 5), dtype=torch.float64).pin_memory(),
-                         torch.empty((B,), dtype=torch.uint8).pin_memory(),
-                         torch.empty((B,), dtype=torch.int32).pin_memory())
-        po, pr, pd, pf = self._pin
+            align = 2 if obs_dtype == torch.float64 else 4   # 16-byte aligned rows: one TMA bulk store per row
+            stride = (self.obs_dynamic_length + align - 1) & ~(align - 1)
+            full = torch.empty((B, stride), dtype=obs_dtype).pin_memory()
+            setattr(self, key, (full, full[:, :self.obs_dynamic_length],
+                                torch.empty((B, 5), dtype=torch.float64).pin_memory(),
+                                torch.empty((B,), dtype=torch.uint8).pin_memory(),
+                                torch.empty((B,), dtype=torch.int32).pin_memory()))
+        full, po, pr, pd, pf = getattr(self, key)
         if actions_pinned is not None and (actions_pinned.dtype != torch.uint8 or not actions_pinned.is_contiguous()
                                            or tuple(actions_pinned.shape) != (self.n_envs, self.action_length)):
             raise ValueError('Expected a contiguous uint8 tensor of shape (%d, %d)' % (self.n_envs, self.action_length))
-        self._check(self.lib.ppn_step_host(self.handle, _ptr(actions_pinned), _ptr(po), self._pin_obs_full.shape[1],
-                                           _ptr(pr), _ptr(pd), _ptr(pf), None, 1 if auto_reset else 0))
+        fn = self.lib.ppn_step_host if obs_dtype == torch.float64 else self.lib.ppn_step_host_f32
+        self._check(fn(self.handle, _ptr(actions_pinned), _ptr(full), full.shape[1], _ptr(pr), _ptr(pd), _ptr(pf), None,
+                       1 if auto_reset else 0))
         return po, pr, pd, pf
 
     # ------------------------------------------------------------------------------------------------------------

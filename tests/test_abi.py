@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(lib):
     from pypownet_b200 import _lib
     with open(os.path.join(ROOT, 'include', 'pypownet_b200.h')) as f:
         header = f.read()
-    declared = set(re.findall(r'\b(ppn_[a-z_]+)\s*\(', header))
+    declared = set(re.findall(r'\b(ppn_[a-z_0-9]+)\s*\(', header))
     assert declared, 'no declarations found'
     assert declared == set(_lib.SYMBOLS), 'binding table and header disagree: %s' % (declared ^ set(_lib.SYMBOLS))
     for name in declared:

@@ -226,6 +226,26 @@ def test_chunked_host_entry_point_is_bit_identical(pinned):
         assert e2.counters()['kernel_launches'] == e1.counters()['kernel_launches']  # zero-copy: one launch
 
 
+def test_float32_observation_rows_are_the_float64_ones_rounded_once():
+    """ppn_step_host_f32 (VecRunEnv.step_pinned(obs_dtype=float32)): same trajectory, every observation value equal to the
+    float64 one narrowed to float32 -- nothing else changes (rewards, done, flags stay float64 / integer)."""
+    fx = Fixture('d14_ac_random')
+    B = 40
+    rng = np.random.default_rng(3)
+    start_r = rng.integers(0, 100, size=B).astype(np.int32)
+    e1 = vec_env(fx, B, start_chronics=np.zeros(B, dtype=np.int32), start_rows=start_r)
+    e2 = vec_env(fx, B, start_chronics=np.zeros(B, dtype=np.int32), start_rows=start_r)
+    nd = fx.case.obs_dynamic_length
+    act = torch.zeros((B, fx.case.action_length), dtype=torch.uint8).pin_memory()
+    for t in range(25):
+        act.copy_(torch.from_numpy(np.repeat(fx.actions[t][None], B, axis=0)))
+        o1, r1, d1, f1 = e1.step_pinned(act, auto_reset=True)
+        o2, r2, d2, f2 = e2.step_pinned(act, auto_reset=True, obs_dtype=torch.float32)
+        assert o2.dtype == torch.float32 and tuple(o2.shape) == (B, nd)
+        assert np.array_equal(o1.numpy().astype(np.float32), o2.numpy()), t
+        assert torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(f1, f2)
+
+
 def test_kernel_written_result_pack_equals_the_three_outputs():
     """ppn_set_result_pack: the row an env-sharded run all-gathers (reward[5] | done | flag) is written by the step
     kernel itself and must equal what packing the three output tensors gives."""
