@@ -74,47 +74,95 @@ def random_action_bank(case, n_envs, n_batches=16, seed=1234):
     return bank
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline (port)
+# ------------------------------------------------------------------------------------- CPU baseline (reference / port)
+# kind "reference": the UNMODIFIED reference package installed in baseline/_ref (tools/install_reference.sh; it travels
+# with the snapshot) on oracle/shims (PYPOWER 5.1.4 slice + gym.spaces restated: neither is installable), one RunEnv per
+# process on the synthetic bench workload written in the reference's on-disk format.  kind "port": oracle/flat.py, the
+# numpy restatement of the same path (5-10x faster per core than the reference), when baseline/_ref is absent.
 _WORKER = {}
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
 
 
-def _cpu_init(grid, counter):
-    """Pool initializer: every process builds the workload and ONE env once (as a reference process would)."""
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, 'pypownet')) and os.environ.get('PPN_CPU_BASELINE', '') != 'port'
+
+
+def _reference_folder(grid):
+    """The synthetic workload as an environment folder of the reference, written once per (grid, machine)."""
+    import tempfile
+    from oracle.ref_folder import write_environment_folder
+    root = os.path.join(tempfile.gettempdir(), 'pypownet_b200_bench_%s_%d' % (grid, os.getuid()))
+    marker = os.path.join(root, '.complete')
+    if not os.path.exists(marker):
+        case, cfg, chronics, imaps = build_workload(grid)
+        for ch in chronics:
+            ch.imaps = np.asarray(imaps, dtype=np.float64)
+        write_environment_folder(root, case, cfg, chronics)      # no reward_signal.py: the reference's own default
+        open(marker, 'w').close()
+    return root
+
+
+def _cpu_init(grid, counter, folder):
+    """Pool initializer: every process builds ONE env once (as a reference process would)."""
     sys.path.insert(0, ROOT)
-    from oracle.flat import FlatEnv, Config
     with counter.get_lock():
         env_id = counter.value
         counter.value += 1
-    case, cfg, chronics, imaps = build_workload(grid)
-    c, r = shard_starts(4096, 0, 1)                     # one env of the 4096-env GPU batch per process
-    k = (257 * env_id) % 4096
-    env = FlatEnv(case, Config(cfg, reward_constant=float(case.n_sub), n_sub=case.n_sub), chronics,
-                  start_id=int(c[k]), thermal_limits=imaps, start_row=int(r[k]))
-    a = np.zeros(case.action_length, dtype=np.uint8)
+    if folder is not None:                                # the unmodified reference
+        import logging
+        import warnings
+        logging.disable(logging.CRITICAL)
+        warnings.simplefilter('ignore')
+        sys.path[:0] = [os.path.join(ROOT, 'oracle', 'shims'), REF_DIR]
+        os.chdir(folder)                                  # the reference writes tmp/ and logs into the cwd
+        from pypownet.environment import RunEnv
+        env = RunEnv(folder, 'level0', start_id=env_id % N_CHRONICS)
+        a = env.action_space.get_do_nothing_action()
+        step = lambda: env.step(a)[2]                     # noqa: E731
+        over = env.process_game_over
+    else:
+        from oracle.flat import FlatEnv, Config
+        case, cfg, chronics, imaps = build_workload(grid)
+        c, r = shard_starts(4096, 0, 1)                   # one env of the 4096-env GPU batch per process
+        k = (257 * env_id) % 4096
+        fenv = FlatEnv(case, Config(cfg, reward_constant=float(case.n_sub), n_sub=case.n_sub), chronics,
+                       start_id=int(c[k]), thermal_limits=imaps, start_row=int(r[k]))
+        a = np.zeros(case.action_length, dtype=np.uint8)
+        step = lambda: fenv.step(a)[2]                    # noqa: E731
+        over = fenv.process_game_over
     for _ in range(5):
-        if env.step(a)[2]:
-            env.process_game_over()
-    _WORKER['env'], _WORKER['action'] = env, a
+        if step():
+            over()
+    _WORKER['step'], _WORKER['over'] = step, over
 
 
 def _cpu_worker(args):
     n_steps, budget_s = args
-    env, a = _WORKER['env'], _WORKER['action']
+    step, over = _WORKER['step'], _WORKER['over']
     t0 = time.perf_counter()
     done_steps = 0
     while done_steps < n_steps and (budget_s is None or time.perf_counter() - t0 < budget_s):
-        if env.step(a)[2]:
-            env.process_game_over()
+        if step():
+            over()
         done_steps += 1
     return done_steps, time.perf_counter() - t0
 
 
 def cpu_pool(grid, cores=None):
+    """(pool, cores, kind).  The unmodified reference when baseline/_ref is installed, else the port."""
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context('spawn')
-    pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(grid, ctx.Value('i', 0)))
+    if reference_available():
+        try:
+            folder = _reference_folder(grid)
+            pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(grid, ctx.Value('i', 0), folder))
+            pool.map(_cpu_worker, [(1, None)] * cores)
+            return pool, cores, 'reference'
+        except Exception as exc:                          # e.g. a box without PyYAML: fall back to the port, loudly
+            sys.stderr.write('reference CPU arm unavailable (%r), timing the port instead\n' % (exc,))
+    pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(grid, ctx.Value('i', 0), None))
     pool.map(_cpu_worker, [(1, None)] * cores)          # make sure every process is up before anything is timed
-    return pool, cores
+    return pool, cores, 'port'
 
 
 def cpu_baseline(pool, cores, steps_per_proc, budget_s=None):
@@ -177,10 +225,10 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    per_step = 100                                       # env-steps per process per bench step (bounded sample)
-    pool, cores = cpu_pool(args.grid)
+    pool, cores, kind = cpu_pool(args.grid)
+    per_step = 20 if kind == 'reference' else 100        # env-steps per process per bench step (bounded sample)
     for _ in range(args.warmup):
-        cpu_baseline(pool, cores, 10)
+        cpu_baseline(pool, cores, 2 if kind == 'reference' else 10)
     total = 0
     busy = 0.0
     for _ in range(args.steps):
@@ -189,18 +237,20 @@ def run_reference(args):
         busy += b
     pool.close()
     value = total / busy
-    sample = '%d processes (one env each) x %d do-nothing env-steps of %s per bench step, synthetic chronics' % (
-        cores, per_step, args.grid)
+    what = 'the UNMODIFIED reference package (baseline/_ref) on oracle/shims' if kind == 'reference' else \
+        'oracle/flat.py, the numpy restatement of the reference path'
+    sample = '%d processes (one env each) x %d do-nothing env-steps of %s per bench step, synthetic chronics; %s' % (
+        cores, per_step, args.grid, what)
     cfg = workload_config(args, None)
     cfg['workload'] = 'CPU arm: %s AC, do-nothing agent, restart on game over; BOUNDED SAMPLE of the 4096-env workload: ' \
-                      '%d single-env processes x %d env-steps per bench step (oracle/flat.py on the host cores)' % (
-                          GRIDS[args.grid], cores, per_step)
+                      '%d single-env processes x %d env-steps per bench step (%s on the host cores)' % (
+                          GRIDS[args.grid], cores, per_step, what)
     line = {'impl': 'reference', 'metric': 'env steps/sec (batched grids)', 'value': value, 'unit': 'env-steps/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': 1e3 * busy / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': cfg,
-            'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -514,13 +564,15 @@ def run_b200(args):
     if secondary:
         line['secondary'] = secondary
     if world == 1 and not args.no_cpu:
-        pool, cores = cpu_pool(args.grid)
+        pool, cores, kind = cpu_pool(args.grid)
         v, n, busy = cpu_baseline(pool, cores, 10 ** 9, budget_s=args.cpu_seconds)
         pool.close()
-        line['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                                'sample': '%d processes x %.0f s of do-nothing env-steps of %s (oracle/flat.py, the '
-                                          'CPU restatement of the reference path), %d env-steps in total'
-                                          % (cores, args.cpu_seconds, args.grid, n)}
+        line['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': kind,
+                                'sample': '%d processes x %.0f s of do-nothing env-steps of %s (%s), %d env-steps in total'
+                                          % (cores, args.cpu_seconds, args.grid,
+                                             'the unmodified reference package in baseline/_ref on oracle/shims'
+                                             if kind == 'reference' else
+                                             'oracle/flat.py, the CPU restatement of the reference path', n)}
     print(json.dumps(line))
     if world > 1:
         ctx.dist.destroy_process_group()

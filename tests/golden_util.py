@@ -72,43 +72,5 @@ def _chronic_from_arrays(name, tabs, ids, datetimes, imaps):
 def write_environment_folder(fx, root):
     """An environment folder in the reference's on-disk format (Appendix B of SURVEY.md) from a fixture, so that
     RunEnv(parameters_folder, 'level0') can be pointed at it.  Returns the parameters folder."""
-    import datetime
-
-    import yaml
-
-    from pypownet_b200.case import write_case_file
-    level = os.path.join(root, 'level0')
-    os.makedirs(os.path.join(level, 'chronics'), exist_ok=True)
-    write_case_file(os.path.join(level, 'reference_grid.py'), fx.case.ppc)
-    with open(os.path.join(level, 'configuration.yaml'), 'w') as f:
-        yaml.safe_dump(fx.config, f)
-    if fx.default_reward:
-        with open(os.path.join(root, 'reward_signal.py'), 'w') as f:
-            f.write('from pypownet_b200.reward_signal import DefaultRewardSignal\n\n\n'
-                    'class CustomRewardSignal(DefaultRewardSignal):\n'
-                    '    def __init__(self):\n        super().__init__(constant=%r)\n' % fx.reward_constant)
-    names = {'prods_p': '_N_prods_p.csv', 'prods_v': '_N_prods_v.csv', 'loads_p': '_N_loads_p.csv',
-             'loads_q': '_N_loads_q.csv', 'prods_p_planned': '_N_prods_p_planned.csv',
-             'prods_v_planned': '_N_prods_v_planned.csv', 'loads_p_planned': '_N_loads_p_planned.csv',
-             'loads_q_planned': '_N_loads_q_planned.csv', 'maintenance': 'maintenance.csv', 'hazards': 'hazards.csv'}
-    for ch in fx.chronics:
-        d = os.path.join(level, 'chronics', ch.name)
-        os.makedirs(d, exist_ok=True)
-        for t, fn in names.items():
-            a = np.asarray(getattr(ch, t), dtype=np.float32)
-            if t.endswith('_planned'):                     # undo `planned[t] := planned[t+1]` (chronic.py:202-205)
-                a = np.vstack([a[:1], a[:-1]])
-            with open(os.path.join(d, fn), 'w') as f:
-                f.write(';'.join('c%d' % i for i in range(a.shape[1])) + '\n')
-                for row in a:
-                    f.write(';'.join(repr(float(v)) for v in row) + '\n')
-        with open(os.path.join(d, '_N_simu_ids.csv'), 'w') as f:
-            f.write('simu_id\n' + '\n'.join('%.1f' % i for i in ch.ids) + '\n')
-        with open(os.path.join(d, '_N_imaps.csv'), 'w') as f:
-            f.write(';'.join('c%d' % i for i in range(len(ch.imaps))) + '\n' +
-                    ';'.join(repr(float(v)) for v in ch.imaps) + '\n')
-        with open(os.path.join(d, '_N_datetimes.csv'), 'w') as f:
-            f.write('date;time\n')
-            for y, mo, dd, h, mi, s in ch.datetimes:
-                f.write(datetime.datetime(y, mo, dd, h, mi).strftime('%Y-%b-%d;%H:%M').lower() + '\n')
-    return root
+    from oracle.ref_folder import write_environment_folder as write
+    return write(root, fx.case, fx.config, fx.chronics, fx.reward_constant if fx.default_reward else None)
