@@ -364,7 +364,7 @@ def measure(ctx, grid, envs, agent, cascade, steps, warmup, with_e2e=True, sampl
     # Sharded runs: every rank's step kernel stores its packed (reward[5], done, flag) rows straight into rank 0's
     # GPU memory over NVLink (sharding.PeerGather); rank 0 copies the rows of step t-1 to the host on a side stream
     # while step t computes.  No collective between two steps: ranks never run in lock-step.
-    pg = sharding.PeerGather(env, rank, world) if world > 1 else None
+    pg = sharding.PeerGather(env, rank, world, ring=16) if world > 1 else None   # 16 slots: a rank may run 16 steps ahead
     tstep = [0]
 
     def one_step():
@@ -528,6 +528,13 @@ def run_b200(args):
                               'algorithmic_bytes_per_env_step': r['algorithmic_bytes_per_env_step'],
                               'gpu_launches': r['launches'], 'per_rank_ms_per_step': r['per_rank_ms_per_step'],
                               'counters': r['counters']})
+    # one GPU only: the same kernel on round 1's env starts (contiguous row windows), for round-to-round comparison
+    r1w = None
+    if world == 1 and not args.no_secondary and args.sharding == 'spread' and not args.emulate_shard:
+        r = measure(ctx, args.grid, args.envs, args.agent, args.cascade, max(10, min(args.steps, 50)), 3, with_e2e=False,
+                    sharding_mode='blocks')
+        r1w = {'value': r['value'], 'ms_per_step': r['ms_per_step'],
+               'note': 'env e -> chronic e mod 12, row e // 12 (the windows BENCH_r01 was measured on)'}
     clocks = sampler.stop() if sampler else None          # sampled over every timed loop of this run
     if args.profile_ranks and rank == 0:
         with open(args.profile_ranks, 'a') as f:
@@ -553,6 +560,8 @@ def run_b200(args):
                   'per_rank_ms_per_step': m['per_rank_ms_per_step'],
                   'per_rank_e2e_d2h_gbs': m['per_rank_e2e_d2h_gbs'],
                   'e2e_float32_observations': m['e2e_f32']})
+    if r1w:
+        extra['same_kernel_on_round1_env_starts'] = r1w
     line = {'metric': 'env steps/sec (batched grids)', 'value': m['value'], 'unit': 'env-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': m['ms_per_step'],
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',

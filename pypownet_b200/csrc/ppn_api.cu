@@ -34,6 +34,7 @@ struct ppn_env {
     int horizon = 20;
     int sp_need[2] = {0, 0};   // doubles of factor storage (both matrices) of the U / F sparse structures
     int sp_blob_dbl[2] = {0, 0};   // doubles of their index tables
+    int sp_hyb_dbl[2] = {0, 0};    // ... of the prefix the hybrid solver stages
     int sparse = 0;            // solver mode of PpnStepArgs.sparse
     int alt_sparse = 0, alt_mat_cap = 0, alt_env_smem_bytes = 0, alt_tpe = 0;   // plan used once buses may be split
     double* pack_dev = nullptr;   // optional packed result rows written by ppn_step (ppn_set_result_pack)
@@ -104,7 +105,54 @@ struct SparseHost {
     std::vector<short> bus_row, rowidx, ecol, parent, row_lev, rowoff;
     std::vector<int> rpack, rowpk, colpk;
     std::vector<int> colptr, lev_ptr, lev_ent, trip_ptr, trip, line_pos, rowptr, rowent, lev_rows_ptr, lev_rows;
+    std::vector<int> wsched;   // one-warp schedule of the hybrid solve (PpnDevSparse.o_wsched); empty: not available
 };
+
+// One-warp schedule of the hybrid solve for the cut at level `cut`: see PpnDevSparse.o_wsched.
+static void build_warp_schedule(SparseHost& h, int cut) {
+    h.wsched.clear();
+    const int n = h.n, r0 = h.lev_rows_ptr[cut], nt = n - r0;
+    if (h.nnz >= 511 || n > 128 || nt > 32 || cut < 1) return;   // 16-bit entries: 9 bits of entry id, 7 of row / column
+    struct Step { int row0, rows, maxcnt; std::vector<std::vector<int>> ent; };   // ent[lane] = packed entries
+    std::vector<Step> fwd, bwd;
+    auto add_rows = [&](std::vector<Step>& dst, int a, int b, bool forward, int col_limit) {
+        for (int base = a; base < b; base += 32) {
+            Step st; st.row0 = base; st.rows = std::min(32, b - base); st.maxcnt = 0; st.ent.resize(32);
+            for (int l = 0; l < st.rows; l++) {
+                const int i = base + l;
+                if (forward) {
+                    for (int t = h.rowptr[i]; t < h.rowptr[i + 1]; t++) {
+                        const int e = h.rowent[t], col = h.ecol[e];
+                        if (col < col_limit) st.ent[l].push_back((e << 7) | col);
+                    }
+                } else {
+                    for (int e = h.colptr[i]; e < h.colptr[i + 1]; e++) st.ent[l].push_back((e << 7) | h.rowidx[e]);
+                }
+                st.maxcnt = std::max(st.maxcnt, (int)st.ent[l].size());
+            }
+            dst.push_back(st);
+        }
+    };
+    for (int lv = 1; lv < cut; lv++) add_rows(fwd, h.lev_rows_ptr[lv], h.lev_rows_ptr[lv + 1], true, n);
+    add_rows(fwd, r0, n, true, r0);                                     // top block: y2 = w2 - L21 y1
+    for (int lv = cut - 1; lv >= 0; lv--) add_rows(bwd, h.lev_rows_ptr[lv], h.lev_rows_ptr[lv + 1], false, 0);
+    std::vector<Step> all(fwd);
+    all.insert(all.end(), bwd.begin(), bwd.end());
+    std::vector<unsigned short> ent;
+    std::vector<int> hdr;
+    for (const Step& st : all) {
+        hdr.push_back(st.row0 | (st.rows << 16));
+        hdr.push_back(st.maxcnt | ((int)ent.size() << 8));
+        for (int q = 0; q < st.maxcnt; q++)
+            for (int l = 0; l < 32; l++) ent.push_back(q < (int)st.ent[l].size() ? (unsigned short)st.ent[l][q] : (unsigned short)0xffff);
+    }
+    h.wsched.push_back((int)fwd.size());
+    h.wsched.push_back((int)bwd.size());
+    h.wsched.insert(h.wsched.end(), hdr.begin(), hdr.end());
+    const size_t w0 = h.wsched.size();
+    h.wsched.resize(w0 + (ent.size() + 1) / 2, 0);
+    memcpy(h.wsched.data() + w0, ent.data(), ent.size() * sizeof(unsigned short));
+}
 
 static std::vector<int> min_degree_order(int S, int N, const int* lor, const int* lex) {
     std::vector<char> a((size_t)S * S, 0), alive(S, 1);
@@ -404,6 +452,37 @@ extern "C" int ppn_sparse_selfcheck(int n_sub, int n_line, const int32_t* line_o
                 w[i] = acc;
             }
         for (int i = 0; i < n; i++) err = fmax(err, fabs(w[i] - xref[i]));
+        // (3) the same solve through the one-warp schedule (PpnDevSparse.o_wsched), step by step as the kernel walks it
+        build_warp_schedule(h, cut);
+        if (!h.wsched.empty()) {
+            const int* ws = h.wsched.data();
+            const int nf = ws[0], nb = ws[1];
+            const int* S = ws + 2;
+            const unsigned short* E = reinterpret_cast<const unsigned short*>(ws + 2 + 2 * (nf + nb));
+            std::vector<double> v = rhs, tmp(32);
+            auto run = [&](int s, bool backward) {
+                const int row0 = S[2 * s] & 0xffff, rows = S[2 * s] >> 16, maxcnt = S[2 * s + 1] & 255, off = S[2 * s + 1] >> 8;
+                for (int l = 0; l < rows; l++) {
+                    double acc = backward ? v[row0 + l] / dg[row0 + l] : v[row0 + l];
+                    for (int q = 0; q < maxcnt; q++) {
+                        const unsigned p0 = E[off + q * 32 + l];
+                        if (p0 != 0xffffu) acc -= Lv[p0 >> 7] * v[p0 & 127u];
+                    }
+                    tmp[l] = acc;
+                }
+                for (int l = 0; l < rows; l++) v[row0 + l] = tmp[l];
+            };
+            for (int s2 = 0; s2 < nf; s2++) run(s2, false);
+            std::vector<double> x2(nt);
+            for (int t = 0; t < nt; t++) {
+                double x = 0.0;
+                for (int j = 0; j < nt; j++) x += Z[(size_t)t * nt + j] * v[r0 + j];
+                x2[t] = x;
+            }
+            for (int t = 0; t < nt; t++) v[r0 + t] = x2[t];
+            for (int s2 = nf; s2 < nf + nb; s2++) run(s2, true);
+            for (int i = 0; i < n; i++) err = fmax(err, fabs(v[i] - xref[i]));
+        }
     }
     *max_err_out = err;
     return PPN_OK;
@@ -535,19 +614,29 @@ static int create_body(const ppn_case* g, const ppn_config* cfg, int n_envs, int
                 if (!v.empty()) memcpy(blob.data() + o, v.data(), v.size() * sizeof(short));
                 return o;
             };
-            d.o_colptr = put_i(h.colptr); d.o_lev_ptr = put_i(h.lev_ptr); d.o_lev_ent = put_i(h.lev_ent);
+            // the tables the hybrid solver reads come first: a CTA stages only that prefix (hyb_words)
+            build_warp_schedule(h, cut);
+            d.o_lev_ptr = put_i(h.lev_ptr); d.o_lev_ent = put_i(h.lev_ent);
             d.o_trip_ptr = put_i(h.trip_ptr); d.o_trip = put_i(h.trip); d.o_line_pos = put_i(h.line_pos);
+            d.o_lev_rows_ptr = put_i(h.lev_rows_ptr);
+            d.o_rowidx = put_s(h.rowidx); d.o_ecol = put_s(h.ecol); d.o_bus_row = put_s(h.bus_row);
+            d.o_wsched = h.wsched.empty() ? -1 : put_i(h.wsched);
+            if (blob.size() & 1) blob.push_back(0);
+            d.hyb_words = (int)blob.size();
+            d.o_colptr = put_i(h.colptr);
             d.o_rowptr = put_i(h.rowptr); d.o_rowent = put_i(h.rowent);
-            d.o_lev_rows_ptr = put_i(h.lev_rows_ptr); d.o_lev_rows = put_i(h.lev_rows); d.o_rpack = put_i(h.rpack);
+            d.o_lev_rows = put_i(h.lev_rows); d.o_rpack = put_i(h.rpack);
             d.o_rowpk = put_i(h.rowpk); d.o_colpk = put_i(h.colpk);
-            d.o_rowidx = put_s(h.rowidx); d.o_ecol = put_s(h.ecol); d.o_parent = put_s(h.parent); d.o_bus_row = put_s(h.bus_row);
+            d.o_parent = put_s(h.parent);
             d.o_row_lev = put_s(h.row_lev); d.o_rowoff = put_s(h.rowoff);
             if (blob.size() & 1) blob.push_back(0);
             d.blob_words = (int)blob.size();
+            if (d.o_wsched < 0) d.hyb_words = d.blob_words;   // the level-by-level solve reads the packed row / column views
             int* bp32;
             UP(bp32, blob); d.blob = bp32;
             env->sp_need[f] = 2 * ppn_sp_factor_doubles(h.n, h.nnz) + 2 * d.nt * (d.nt | 1);   // + the dense top blocks
             env->sp_blob_dbl[f] = d.blob_words / 2;
+            env->sp_hyb_dbl[f] = d.hyb_words / 2;
         }
     }
 
@@ -629,7 +718,7 @@ static int create_body(const ppn_case* g, const ppn_config* cfg, int n_envs, int
             const PpnDevSparse& u = env->dc.sp[0];
             want = (n1 + 1) * (n1 | 1) + (n2 + 1) * (n2 | 1) + 2 * ppn_sp_factor_doubles(u.n, u.nnz);
         }
-        if (mode >= 2) want = env->sp_need[0] + env->sp_blob_dbl[0];
+        if (mode >= 2) want = env->sp_need[0] + (mode == 3 ? env->sp_hyb_dbl[0] : env->sp_blob_dbl[0]);
         if (cfg->pf_alg == 1 && tpe <= 32) {   // Newton-Raphson: the Jacobian of the un-split grid + right-hand side
             const int nj = n1 + n2;
             if (want < nj * (nj + 1)) want = nj * (nj + 1);

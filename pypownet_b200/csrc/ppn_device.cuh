@@ -33,6 +33,14 @@ struct PpnDevSparse {
     int cut_ent;              // first entry whose column belongs to the block (entries are column-major)
     int nt;                   // rows of the block
     int blob_words;           // 32-bit words of the table blob
+    int hyb_words;            // words of its prefix the hybrid solver needs (the tables it uses come first; = blob_words
+                              // when the warp schedule below is not available)
+    int o_wsched;             // int, or -1: the hybrid SOLVE as a schedule for ONE warp, a row per lane, every step's
+                              // entries laid out lane-major so that no index load depends on another one:
+                              //   [0] forward steps (sparse levels 1..cut-1, then the rows of the top block gathering
+                              //   the columns below the cut), [1] backward steps (levels cut-1..0), then per step
+                              //   (first row | rows << 16), (entries per row | halfword offset << 8), then the 16-bit
+                              //   entries (entry id << 7 | column or row), 0xffff = none, 32 per (step, entry slot)
     const int* blob;          // every table below in one contiguous block, so that a CTA can stage it in shared memory
     // word offsets into the blob (int tables first, then the short tables)
     int o_colptr;             // int   [n+1]  off-diagonal entries of L by column, rows ascending

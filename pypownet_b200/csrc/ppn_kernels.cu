@@ -418,6 +418,12 @@ __device__ __forceinline__ int lds16(unsigned a) {
     return (int)v;
 }
 
+__device__ __forceinline__ unsigned lds16u(unsigned a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return (unsigned)v;
+}
+
 struct SpsFactor { unsigned T, Lv, dg; };   // shared-window addresses of one factor's arrays
 
 template <int TPE> __device__ __forceinline__ void sps_factor2(const PpnDevSparse& sp, unsigned tb, const SpsFactor& f1, const SpsFactor& f2,
@@ -722,6 +728,71 @@ template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp
         }
     }
     __syncthreads();
+}
+
+// The same solve as ONE-WARP PROGRAM driven by the static schedule PpnDevSparse.o_wsched: a row per lane in every step,
+// the entries of a step laid out lane-major (16-bit: entry id << 7 | row or column), so that within a step no index load
+// depends on another one -- header and entries are fetched while the previous step's stores drain, the only chain is
+// operand load -> FMA -> store -> __syncwarp.  The dense top block (nt <= 32 rows) is one more step of the same warp:
+// no CTA barrier inside the solve at all; the other warps wait at the closing barrier without using issue slots.
+template <int TPE> __device__ __noinline__ void hyb_solve_warp(const PpnDevSparse& sp, unsigned tb, unsigned a_Lv, unsigned a_dg, const double* Z,
+                                                                  int ldz, unsigned a_w, int tid) {
+    if (tid < 32) {
+        const unsigned ws = tb + 4u * sp.o_wsched;
+        const int nf = lds32(ws), nb = lds32(ws + 4u);
+        const unsigned a_hdr = ws + 8u, a_ent = a_hdr + 8u * (unsigned)(nf + nb), a_z = saddr(Z);
+        const int r0 = sp.cut_row, nt = sp.nt;
+        int h0 = lds32(a_hdr), h1 = lds32(a_hdr + 4u);
+        for (int st = 0; st < nf + nb; st++) {
+            if (st == nf) {   // x2 = Z y2 between the forward and the backward steps
+                double x = 0.0, x2 = 0.0;
+                if (tid < nt) {
+                    const unsigned zr = a_z + 8u * (unsigned)(tid * ldz), wr = a_w + 8u * r0;
+                    int j = 0;
+#pragma unroll 1
+                    for (; j + 1 < nt; j += 2) {
+                        x = fma(lds64(zr + 8u * j), lds64(wr + 8u * j), x);
+                        x2 = fma(lds64(zr + 8u * j + 8u), lds64(wr + 8u * j + 8u), x2);
+                    }
+                    if (j < nt) x = fma(lds64(zr + 8u * j), lds64(wr + 8u * j), x);
+                    x += x2;
+                }
+                __syncwarp();
+                if (tid < nt) sts64(a_w + 8u * (r0 + tid), x);
+                __syncwarp();
+            }
+            const int row0 = h0 & 0xffff, rows = h0 >> 16, maxcnt = h1 & 255;
+            unsigned ea = a_ent + 2u * ((unsigned)(h1 >> 8) + (unsigned)tid);
+            if (st + 1 < nf + nb) { h0 = lds32(a_hdr + 8u * (st + 1)); h1 = lds32(a_hdr + 8u * (st + 1) + 4u); }   // next header
+            const bool mine = tid < rows;
+            const unsigned wi = a_w + 8u * (unsigned)(row0 + tid);
+            double acc = 0.0, acc2 = 0.0;
+            if (mine) acc = st >= nf ? lds64(wi) * lds64(a_dg + 8u * (unsigned)(row0 + tid)) : lds64(wi);
+            int q = 0;
+#pragma unroll 1
+            for (; q + 1 < maxcnt; q += 2, ea += 128u) {   // 32 halfwords per entry slot
+                const unsigned p0 = lds16u(ea), p1 = lds16u(ea + 64u);
+                const double l0 = p0 != 0xffffu ? lds64(a_Lv + 8u * (p0 >> 7)) : 0.0, v0 = p0 != 0xffffu ? lds64(a_w + 8u * (p0 & 127u)) : 0.0;
+                const double l1 = p1 != 0xffffu ? lds64(a_Lv + 8u * (p1 >> 7)) : 0.0, v1 = p1 != 0xffffu ? lds64(a_w + 8u * (p1 & 127u)) : 0.0;
+                acc = fma(-l0, v0, acc);
+                acc2 = fma(-l1, v1, acc2);
+            }
+            if (q < maxcnt) {
+                const unsigned p0 = lds16u(ea);
+                if (p0 != 0xffffu) acc = fma(-lds64(a_Lv + 8u * (p0 >> 7)), lds64(a_w + 8u * (p0 & 127u)), acc);
+            }
+            if (mine) sts64(wi, acc + acc2);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+// the one-warp schedule when the structure has one (16-bit entries: < 511 fill entries, <= 128 rows, top block <= 32)
+template <int TPE> __device__ __forceinline__ void hyb_solve_any(const PpnDevSparse& sp, unsigned tb, unsigned a_Lv, unsigned a_dg, const double* Z,
+                                                                 int ldz, unsigned a_w, int tid) {
+    if (sp.o_wsched >= 0) hyb_solve_warp<TPE>(sp, tb, a_Lv, a_dg, Z, ldz, a_w, tid);
+    else hyb_solve<TPE>(sp, tb, a_Lv, a_dg, Z, ldz, a_w, tid);
 }
 
 // L D L^T x = w in place; dg holds the RECIPROCAL pivots.  The rows of a level are contiguous (the host sorts the
@@ -1170,7 +1241,7 @@ __device__ __forceinline__ bool dc_solve(Env<TPE, D>& e, const PpnDevCase& c, do
         const SpsFactor s1{saddr(f1.T), saddr(f1.Lv), saddr(f1.dg)}, s2{saddr(f2.T), saddr(f2.Lv), saddr(f2.dg)};
         hyb_factor2<TPE>(*sp->d, sp->tb, s1, s2, Z1, Z1 + sp->d->nt * ldz, ldz, tid);
         hyb_invert2<TPE>(Z1, Z1 + sp->d->nt * ldz, sp->d->nt, ldz, e.vri(), tid);   // vri: 2 NB doubles of scratch in DC mode
-        hyb_solve<TPE>(*sp->d, sp->tb, s1.Lv, s1.dg, Z1, ldz, saddr(e.ydr()), tid);
+        hyb_solve_any<TPE>(*sp->d, sp->tb, s1.Lv, s1.dg, Z1, ldz, saddr(e.ydr()), tid);
         for (int i = tid; i < n1; i += TPE) e.Q()[i] = e.ydr()[sp->bus_row[e.busp()[i]]];
     } else if (solve_mode) {
         sp_factor<TPE, 1>(*sp, f1, f1, tid, mask);
@@ -1387,7 +1458,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                 if (TPE > 32 && sp->hyb) {
                     const int ldz = sp->d->nt | 1;
                     const double* Zh = spb + 2 * ppn_sp_factor_doubles(sp->n, sp->nnz) + ((half & 1) ? 0 : sp->d->nt * ldz);
-                    hyb_solve<TPE>(*sp->d, sp->tb, saddr(fh.Lv), saddr(fh.dg), Zh, ldz, saddr(wh), tid);
+                    hyb_solve_any<TPE>(*sp->d, sp->tb, saddr(fh.Lv), saddr(fh.dg), Zh, ldz, saddr(wh), tid);
                     const int m = (half & 1) ? 0 : 1;
                     if (bd && bd->k[m] > 0) {   // y = S^-1 (g - B^T t), x = t - W y
                         const int nU = sp->n, kh = bd->k[m];
@@ -1515,7 +1586,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                         for (int j = 0; j < bd->k[m]; j++) {
                             for (int i = tid; i < nU; i += TPE) col[i] = bd->W[m][j * nU + i];
                             __syncthreads();
-                            hyb_solve<TPE>(*sp->d, sp->tb, saddr(fm.Lv), saddr(fm.dg), Zm, ldz, saddr(col), tid);
+                            hyb_solve_any<TPE>(*sp->d, sp->tb, saddr(fm.Lv), saddr(fm.dg), Zm, ldz, saddr(col), tid);
                             for (int i = tid; i < nU; i += TPE) bd->W[m][j * nU + i] = col[i];
                             __syncthreads();
                         }
@@ -1985,14 +2056,15 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
         // hybrid factor, AC: a handful of sister buses border the one-row-per-substation factor (see Border) instead of
         // moving the env to the two-rows-per-substation structure
         const bool bordered = TPE > 32 && args.sparse == 3 && !cfg.dc && n_sis > 0 && n_sis <= PPN_BORDER_MAX &&
-                              2 * ppn_sp_factor_doubles(c.sp[0].n, c.sp[0].nnz) + 2 * c.sp[0].nt * (c.sp[0].nt | 1) + c.sp[0].blob_words / 2 <= args.mat_cap &&
+                              2 * ppn_sp_factor_doubles(c.sp[0].n, c.sp[0].nnz) + 2 * c.sp[0].nt * (c.sp[0].nt | 1) + c.sp[0].hyb_words / 2 <= args.mat_cap &&
                               2 * PPN_BORDER_MAX * c.sp[0].n + 2 * PPN_BORDER_MAX * PPN_BORDER_MAX <= args.ws_stride;   // the hybrid plan is in place
         const int which = (n_sis > 0 && !bordered) ? 1 : 0;
         const PpnDevSparse& spd = c.sp[which];
         const bool solve_mode = args.sparse >= 2;
         const int dense_need = solve_mode ? 0 : (n1 + 1) * ld1 + (cfg.dc ? 0 : (n2 + 1) * ld2);
         const int val_need = 2 * ppn_sp_factor_doubles(spd.n, spd.nnz) + (args.sparse == 3 ? 2 * spd.nt * (spd.nt | 1) : 0),
-                  blob_dbl = spd.blob_words / 2;
+                  stage_words = args.sparse == 3 ? spd.hyb_words : spd.blob_words,   // the hybrid solver only reads a prefix
+                  blob_dbl = stage_words / 2;
         double* wsrow = args.ws + (size_t)slot * args.ws_stride;
         // index tables: staged once per CTA at the end of the matrix area when everything fits (they stay there
         // across the load-flows of this step), else read from global memory
@@ -2001,7 +2073,7 @@ __device__ __forceinline__ bool loadflow(Env<TPE, D>& e, const PpnDevCase& c, co
             int* dst = reinterpret_cast<int*>(e.mat() + (args.mat_cap - blob_dbl));
             if (e.misc()[3] != which) {
                 env_sync<TPE>(mask);
-                for (int i = tid; i < spd.blob_words; i += TPE) dst[i] = spd.blob[i];
+                for (int i = tid; i < stage_words; i += TPE) dst[i] = spd.blob[i];
                 if (tid == 0) e.misc()[3] = which;
                 env_sync<TPE>(mask);
             }

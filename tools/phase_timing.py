@@ -4,7 +4,7 @@ import ctypes, os, subprocess, sys
 import numpy as np, torch
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 sys.path.insert(0, ROOT)
-lib_dbg = os.path.join(ROOT, 'build', 'libpypownet_b200_timing.so')   # build it in the container: it travels with the snapshot
+lib_dbg = os.path.join(ROOT, 'pypownet_b200', 'libpypownet_b200_timing.so')   # built in the container; *.so travel with the snapshot
 import __graft_entry__ as g
 if not os.path.exists(lib_dbg) or '--build' in sys.argv:
     os.makedirs(os.path.dirname(lib_dbg), exist_ok=True)
