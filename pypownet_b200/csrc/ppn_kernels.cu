@@ -735,7 +735,7 @@ template <int TPE> __device__ __noinline__ void hyb_solve(const PpnDevSparse& sp
 // depends on another one -- header and entries are fetched while the previous step's stores drain, the only chain is
 // operand load -> FMA -> store -> __syncwarp.  The dense top block (nt <= 32 rows) is one more step of the same warp:
 // no CTA barrier inside the solve at all; the other warps wait at the closing barrier without using issue slots.
-template <int TPE> __device__ __noinline__ void hyb_solve_warp(const PpnDevSparse& sp, unsigned tb, unsigned a_Lv, unsigned a_dg, const double* Z,
+template <int TPE> __device__ __forceinline__ void hyb_solve_warp(const PpnDevSparse& sp, unsigned tb, unsigned a_Lv, unsigned a_dg, const double* Z,
                                                                   int ldz, unsigned a_w, int tid) {
     if (tid < 32) {
         const unsigned ws = tb + 4u * sp.o_wsched;
@@ -2298,7 +2298,8 @@ __device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCa
 // ------------------------------------------------------------------------------------------------------ the kernel
 template <int TPE, int MAXR, class D, int MINB>
 __global__ void __launch_bounds__(TPE <= 32 ? 64 : TPE, MINB)
-ppn_step_kernel(PpnDevCase c, PpnDevChronics ch, PpnDevCfg cfg, PpnDevState st, PpnStepArgs args, int env_smem_bytes) {
+ppn_step_kernel(const __grid_constant__ PpnDevCase c, const __grid_constant__ PpnDevChronics ch, const __grid_constant__ PpnDevCfg cfg,
+                const __grid_constant__ PpnDevState st, const __grid_constant__ PpnStepArgs args, int env_smem_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int envs_per_block = TPE <= 32 ? (blockDim.x / TPE) : 1;
     const int local = TPE <= 32 ? (threadIdx.x / TPE) : 0;
