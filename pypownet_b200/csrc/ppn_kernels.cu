@@ -2312,7 +2312,12 @@ ppn_step_kernel(const __grid_constant__ PpnDevCase c, const __grid_constant__ Pp
     e.tid = TPE <= 32 ? (threadIdx.x & (TPE - 1)) : threadIdx.x;
     e.shift = TPE < 32 ? ((threadIdx.x & 31) & ~(TPE - 1)) : 0;
     e.mask = TPE < 32 ? (((1u << TPE) - 1u) << e.shift) : PPN_FULL;
-    e.base = smem_raw + (size_t)local * env_smem_bytes;
+    {   // the env's shared-memory image: its base address is made opaque to the optimiser, which otherwise re-derives it
+        // from %tid / the CTA's shared window / env_smem_bytes at every use (7 instructions, dozens of times per iteration)
+        unsigned bs = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)local * (unsigned)env_smem_bytes;
+        asm volatile("" : "+r"(bs));
+        e.base = reinterpret_cast<unsigned char*>(__cvta_shared_to_generic((size_t)bs));
+    }
     e.fixed_bytes = env_smem_bytes - 8 * args.mat_cap;
     const int tid = e.tid, S = e.S, G = e.G, L = e.L, N = e.N, NB = e.NB;
     const unsigned mask = e.mask;
@@ -2612,7 +2617,8 @@ extern "C" int ppn_launch_step(const PpnDevCase* c, const PpnDevChronics* ch, co
         case 16:   // two envs per warp: measured slower than a warp per env, kept size-generic only
             return launch_group<16, 2, DynDims, 1>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
         case 32:
-            // IEEE-14: 96 registers, ten 64-thread CTAs per SM.  Measured alternatives: 80 registers (12 CTAs) 9.9 M
+            // IEEE-14: 96 registers, ten 64-thread CTAs per SM.  Measured alternatives (round 2: 128 registers, 8 CTAs:
+            // +1.6 % at 4096 envs, -1 % at 65536 -- not kept); round 1: 80 registers (12 CTAs) 9.9 M
             // env-steps/s, 72 registers (14 CTAs, 4096 envs in one wave) 9.2 M, against 10.9 M -- the spills cost more
             // than the second wave
             if (dims_match<Dims14>(c)) return launch_group<32, 2, Dims14, 10>(c, ch, cfg, st, args, envs_per_block, env_smem_bytes, stream);
