@@ -56,6 +56,8 @@ struct ppn_env {
     uint8_t* h_ill = nullptr; uint8_t* d_ill = nullptr;
     int32_t* d_init = nullptr;   // [2B] chronic idx | row0
     cudaStream_t own_stream = nullptr;
+    cudaStream_t drain_stream = nullptr;   // ppn_step_host: the kernel that moves finished rows to the host (see step_host_impl)
+    unsigned* d_row_flag = nullptr; int* d_drain_err = nullptr; unsigned epoch = 0;
     // host-buffer entry point: the batch is cut into chunks, each with its own stream, so that the copies of one chunk
     // overlap the kernels of the others
     static const int MAX_CHUNKS = 16;
@@ -792,6 +794,8 @@ extern "C" void ppn_destroy(ppn_env* env) {
     void* dev[] = {env->d_act, env->d_obs, env->d_reward, env->d_done, env->d_flag, env->d_ill};
     for (void* p : dev) if (p) cudaFree(p);
     if (env->own_stream) cudaStreamDestroy(env->own_stream);
+    if (env->drain_stream) cudaStreamDestroy(env->drain_stream);
+    cudaFree(env->d_row_flag); cudaFreeHost(env->d_drain_err);
     if (env->h_split) cudaFreeHost(env->h_split);
     for (int i = 0; i < env->n_chunks; i++) if (env->chunk_stream[i]) cudaStreamDestroy(env->chunk_stream[i]);
     delete env;
@@ -1023,6 +1027,11 @@ static int ensure_staging(ppn_env* env) {
     CK(cudaMalloc(&env->d_flag, B * sizeof(int32_t)));
     CK(cudaMallocHost(&env->h_ill, B * iw));
     CK(cudaMalloc(&env->d_ill, B * iw));
+    CK(cudaMalloc(&env->d_row_flag, B * sizeof(unsigned)));
+    CK(cudaMemset(env->d_row_flag, 0, B * sizeof(unsigned)));
+    CK(cudaHostAlloc(&env->d_drain_err, sizeof(int), cudaHostAllocMapped));   // read by the host after every step: no copy
+    *env->d_drain_err = 0;
+    CK(cudaStreamCreateWithFlags(&env->drain_stream, cudaStreamNonBlocking));
     // two chunks measured best on B200 (every chunk ends with its own slowest env, so more chunks overlap no more copy
     // time and only add launches); PPN_HOST_CHUNKS overrides the count
     int n = B >= 1024 ? 2 : 1;
@@ -1033,6 +1042,84 @@ static int ensure_staging(ppn_env* env) {
     for (int i = 0; i < n; i++) CK(cudaStreamCreateWithFlags(&env->chunk_stream[i], cudaStreamNonBlocking));
     env->n_chunks = n;
     return PPN_OK;
+}
+
+// ---- drain kernel of the zero-copy host step.  A step CTA that stores its observation row straight into host memory holds
+// its SM slot until PCIe has accepted the row, so the burst of the first wave (every env of a small grid finishes within
+// ~100 us) delays the second wave by the time the link needs for it.  Instead the step kernel writes the row to device memory,
+// release-stores the row's flag and retires; the few warps of this kernel -- launched BEFORE the step kernel on a stream of
+// their own, so they are resident from the start -- poll the flags of their rows and move every finished row to the host
+// while the other envs still iterate.  The step kernel never waits for this one, so there is no deadlock in either launch order;
+// a spin limit (about two seconds) turns a step kernel that never ran into an error instead of a hang.
+#define PPN_DRAIN_MAXJ 4   // rows a lane watches at most
+__global__ void __launch_bounds__(1024) ppn_obs_drain_kernel(const unsigned long long* __restrict__ stage, long long stage_stride8,
+                                                            unsigned long long* __restrict__ host, long long host_stride8, int n_rows,
+                                                            int n8, const unsigned* flags, unsigned epoch, int n_warps, int* error) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= n_warps) return;
+    // lane i watches the flags of rows gw + (i + 32 j) * n_warps, j = 0 .. PPN_DRAIN_MAXJ-1.  Interleaved, because the rows that
+    // finish last (the last wave of step CTAs) are neighbours: contiguous ranges would leave that tail to a few warps
+    unsigned pending[PPN_DRAIN_MAXJ];
+    unsigned any = 0;
+#pragma unroll
+    for (int j = 0; j < PPN_DRAIN_MAXJ; j++) {
+        pending[j] = __ballot_sync(0xffffffffu, gw + (long long)(lane + 32 * j) * n_warps < n_rows);
+        any |= pending[j];
+    }
+    const bool v16 = ((stage_stride8 | host_stride8) & 1) == 0 && ((reinterpret_cast<size_t>(stage) | reinterpret_cast<size_t>(host)) & 15) == 0;
+    const int n16 = n8 >> 1;
+    const long long t0 = clock64();
+    while (any) {
+        unsigned got = 0;
+        any = 0;
+#pragma unroll
+        for (int j = 0; j < PPN_DRAIN_MAXJ; j++) {
+            if (!pending[j]) continue;
+            unsigned f = 0;
+            if ((pending[j] >> lane) & 1u) f = *reinterpret_cast<const volatile unsigned*>(flags + gw + (long long)(lane + 32 * j) * n_warps);
+            const bool here = ((pending[j] >> lane) & 1u) && (f & 0x7fffffffu) == epoch;
+            const unsigned ready = __ballot_sync(0xffffffffu, here);
+            unsigned copy = __ballot_sync(0xffffffffu, here && !(f & 0x80000000u));   // rows that carry an observation
+            pending[j] &= ~ready;
+            any |= pending[j];
+            got |= ready;
+            if (ready) __threadfence();   // acquire side of the row's release store: the row is read after its flag
+            while (copy) {
+                const int i = __ffs(copy) - 1;
+                copy &= copy - 1;
+                const long long row = gw + (long long)(i + 32 * j) * n_warps;
+                const unsigned long long* src = stage + row * stage_stride8;
+                unsigned long long* dst = host + row * host_stride8;
+                if (v16) {
+                    const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);
+                    ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
+                    int k = lane;
+                    for (; k + 224 < n16; k += 256) {   // eight loads in flight per lane
+                        ulonglong2 v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) v[q] = __ldcg(s2 + k + 32 * q);
+#pragma unroll
+                        for (int q = 0; q < 8; q++) d2[k + 32 * q] = v[q];
+                    }
+                    {   // the rest (< 256 elements) with predicated loads, still all in flight together
+                        ulonglong2 v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) if (k + 32 * q < n16) v[q] = __ldcg(s2 + k + 32 * q);
+#pragma unroll
+                        for (int q = 0; q < 8; q++) if (k + 32 * q < n16) d2[k + 32 * q] = v[q];
+                    }
+                    if ((n8 & 1) && lane == 0) dst[n8 - 1] = __ldcg(src + n8 - 1);
+                } else {
+                    for (int k = lane; k < n8; k += 32) dst[k] = __ldcg(src + k);
+                }
+            }
+        }
+        if (any && !got) {
+            if (clock64() - t0 > 4000000000ll) { if (lane == 0) atomicExch(error, 1); return; }
+            __nanosleep(500);
+        }
+    }
 }
 
 // true when p is page-locked host memory the copy engines can reach directly (cudaMallocHost / cudaHostRegister)
@@ -1080,7 +1167,7 @@ static int step_host_impl(ppn_env* env, const uint8_t* act_host, double* obs_hos
     {
         void* outs[5] = {obs_host, reward_host, done_host, flag_host, illegal_host};
         void* dev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-        bool direct = getenv("PPN_HOST_STAGED") == nullptr;
+        bool direct = f32 || getenv("PPN_HOST_STAGED") == nullptr;   // float32 rows only exist on the zero-copy path
         for (int i = 0; i < 5 && direct; i++) {
             if (!outs[i]) continue;
             if (!is_pinned(outs[i]) || cudaHostGetDevicePointer(&dev[i], outs[i], 0) != cudaSuccess) { cudaGetLastError(); direct = false; }
@@ -1095,9 +1182,37 @@ static int step_host_impl(ppn_env* env, const uint8_t* act_host, double* obs_hos
             a.mode = PPN_MODE_STEP; a.auto_reset = auto_reset; a.act = act_host ? env->d_act : nullptr;
             a.obs = (double*)dev[0]; a.obs_stride = obs_stride; a.obs_f32 = f32 ? 1 : 0; a.reward = (double*)dev[1]; a.done = (uint8_t*)dev[2];
             a.flag = (int32_t*)dev[3]; a.illegal = (uint8_t*)dev[4];
+            // rows through device memory + the drain kernel when the link could carry them within the kernel's run time only
+            // if they did not hold SM slots (small rows: the IEEE-14 class); large rows keep the link busy either way
+            const char* drain_env = getenv("PPN_HOST_DRAIN");   // 0 / 1 overrides the choice below
+            const size_t row_bytes = OD * (f32 ? sizeof(float) : sizeof(double));
+            const bool drain = dev[0] && (drain_env ? atoi(drain_env) != 0 : row_bytes <= 4096) && (row_bytes % 8) == 0 &&
+                               (f32 ? (obs_stride % 2) == 0 : true);
+            if (drain) {
+                const int n8 = (int)(row_bytes / 8);
+                const long long ss8 = (long long)OD * (f32 ? 4 : 8) / 8, hs8 = obs_stride * (f32 ? 4 : 8) / 8;
+                // 64 rows per warp, 4 warps per CTA measured best on B200 (more, or larger, drain CTAs slow the step kernel down)
+                static const int rpw = []{ const char* v = getenv("PPN_DRAIN_ROWS"); int r = v ? atoi(v) : 64; return r < 1 ? 1 : (r > 32 * PPN_DRAIN_MAXJ ? 32 * PPN_DRAIN_MAXJ : r); }();
+                static const int blk = []{ const char* v = getenv("PPN_DRAIN_BLOCK"); int r = v ? atoi(v) : 128; return r < 32 ? 32 : (r > 1024 ? 1024 : (r & ~31)); }();
+                const int warps = ((int)B + rpw - 1) / rpw, wpb = blk / 32;
+                env->epoch = (env->epoch + 1) & 0x7fffffffu;
+                if (env->epoch == 0) env->epoch = 1;
+                ppn_obs_drain_kernel<<<(warps + wpb - 1) / wpb, blk, 0, env->drain_stream>>>(
+                    reinterpret_cast<const unsigned long long*>(env->d_obs), ss8, reinterpret_cast<unsigned long long*>(dev[0]), hs8, (int)B,
+                    n8, env->d_row_flag, env->epoch, warps, env->d_drain_err);
+                CK(cudaGetLastError());
+                a.obs = env->d_obs; a.obs_stride = (long long)OD; a.row_flag = env->d_row_flag; a.epoch = env->epoch;
+            }
             rc = launch(env, a, s);
-            if (rc) return rc;
+            if (rc) {
+                if (drain) cudaStreamSynchronize(env->drain_stream);   // gives up after its spin limit
+                return rc;
+            }
             CK(cudaStreamSynchronize(s));
+            if (drain) {
+                CK(cudaStreamSynchronize(env->drain_stream));
+                if (*(volatile int*)env->d_drain_err) { *env->d_drain_err = 0; return fail(env, PPN_E_CUDA, "ppn_step_host: the drain kernel timed out waiting for rows"); }
+            }
             env->async_pending = false;
             return PPN_OK;
         }
@@ -1212,7 +1327,7 @@ __global__ void ppn_peer_wait_kernel(const unsigned long long* flags, int n, uns
         while (true) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + i) : "memory");
             if (v >= value) break;
-            __nanosleep(200);
+            __nanosleep(500);
         }
     }
 }

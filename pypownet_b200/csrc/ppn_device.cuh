@@ -173,6 +173,9 @@ struct PpnStepArgs {
                                 // is a handful of wide parallel steps and no full dense matrix is ever stored
     int mat_cap;                // doubles of shared memory per env for B' and B''
     unsigned long long* stats;  // [8] or NULL
+    unsigned* row_flag;         // [rows] or NULL: after a row's results are complete in (device) memory, its thread 0
+    unsigned epoch;             // release-stores `epoch` there (| 0x80000000 when the row carries no observation): the
+                                // signal the drain kernel of ppn_step_host waits for (ppn_api.cu)
     long long* trace;           // [rows][4] or NULL: clock cycles, load-flows, fast-decoupled iterations and restarts each
                                 // launch row spent in this call (ppn_set_env_trace: where does a step's time go)
     int* split_flag;            // page-locked host word (device alias) set to 1 when an env applies a node switch:

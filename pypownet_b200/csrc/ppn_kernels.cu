@@ -2216,7 +2216,7 @@ __device__ __forceinline__ void reset_grid(Env<TPE, D>& e, const PpnDevCase& c) 
 // a float32 network anyway; every value is the double one rounded once).
 template <int TPE, class D, class T>
 __device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCase& c, const PpnDevChronics& ch, T* out,
-                                                  T* stage, bool bulk) {
+                                                  T* stage, bool bulk, bool wait_written = false) {
     const int G = e.G, L = e.L, N = e.N, S = e.S, tid = e.tid;
     compute_isolated(e);
     const float* row = chronic_row(ch, e.cursor()[0], max(e.cursor()[1], 0));   // maintenance horizon, date
@@ -2285,7 +2285,8 @@ __device__ __forceinline__ void write_observation(Env<TPE, D>& e, const PpnDevCa
                              :: "l"(out), "r"(saddr(stage)), "r"(nb * (int)sizeof(T)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 for (int i = nb; i < n; i++) out[i] = stage[i];
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the source may be reused / freed
+                if (wait_written) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the row is in memory: a flag follows
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // the source may be reused / freed
             }
             env_sync<TPE>(e.mask);
         } else {
@@ -2526,10 +2527,21 @@ ppn_step_kernel(const __grid_constant__ PpnDevCase c, const __grid_constant__ Pp
         flows_ampere(e, c);
         if (args.obs_f32)
             write_observation<TPE, D, float>(e, c, ch, reinterpret_cast<float*>(args.obs) + (size_t)slot * args.obs_stride,
-                                             args.mat_cap >= c.OBSD ? reinterpret_cast<float*>(e.mat()) : nullptr, args.obs_bulk != 0);
+                                             args.mat_cap >= c.OBSD ? reinterpret_cast<float*>(e.mat()) : nullptr, args.obs_bulk != 0,
+                                             args.row_flag != nullptr);
         else
             write_observation<TPE, D, double>(e, c, ch, args.obs + (size_t)slot * args.obs_stride,
-                                              args.mat_cap >= c.OBSD ? e.mat() : nullptr, args.obs_bulk != 0);
+                                              args.mat_cap >= c.OBSD ? e.mat() : nullptr, args.obs_bulk != 0, args.row_flag != nullptr);
+    }
+    if (args.row_flag) {
+        // the row (written through the async proxy by the bulk store, or by plain stores) is complete: publish it
+        env_sync<TPE>(mask);
+        if (tid == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence();
+            const unsigned v = args.epoch | ((args.obs && !done) ? 0u : 0x80000000u);
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(args.row_flag + slot), "r"(v) : "memory");
+        }
     }
     if (!is_sim) {
         env_sync<TPE>(mask);

@@ -226,6 +226,50 @@ def test_chunked_host_entry_point_is_bit_identical(pinned):
         assert e2.counters()['kernel_launches'] == e1.counters()['kernel_launches']  # zero-copy: one launch
 
 
+@pytest.mark.parametrize('drain', ['0', '1'])
+@pytest.mark.parametrize('dtype', ['float64', 'float32'])
+def test_pinned_rows_with_and_without_the_drain_kernel(monkeypatch, drain, dtype):
+    """ppn_step_host with page-locked buffers delivers the observation rows either by stores of the step kernel itself or
+    through device memory + the drain kernel (small rows; PPN_HOST_DRAIN forces either).  Same bits both ways; the row of an
+    env that ended without auto-reset is not written at all."""
+    monkeypatch.setenv('PPN_HOST_DRAIN', drain)
+    fx = Fixture('d14_ac_random')
+    B = 700
+    rng = np.random.default_rng(11)
+    start_r = rng.integers(0, 100, size=B).astype(np.int32)
+    e1 = vec_env(fx, B, start_chronics=np.zeros(B, dtype=np.int32), start_rows=start_r)
+    e2 = vec_env(fx, B, start_chronics=np.zeros(B, dtype=np.int32), start_rows=start_r)
+    case = fx.case
+    nd = case.obs_dynamic_length
+    tdt = torch.float64 if dtype == 'float64' else torch.float32
+    act = torch.zeros((B, case.action_length), dtype=torch.uint8).pin_memory()
+    n_done = 0
+    ended = np.zeros(B, dtype=bool)
+    for t in range(10):
+        a = np.zeros((B, case.action_length), dtype=np.uint8)
+        rows = np.nonzero(rng.random(B) < 0.6)[0]
+        a[rows, case.n_gen + case.n_load + 2 * case.n_line + rng.integers(case.n_line, size=len(rows))] = 1
+        a[ended] = 0
+        act.copy_(torch.from_numpy(a))
+        o1, r1, d1, f1 = e1.step(a, auto_reset=False)
+        if hasattr(e2, '_pin64' if dtype == 'float64' else '_pin32'):
+            getattr(e2, '_pin64' if dtype == 'float64' else '_pin32')[0].fill_(-7.0)
+        po, pr, pd, pf = e2.step_pinned(act, auto_reset=False, obs_dtype=tdt)
+        d = d1.cpu().numpy().astype(bool)
+        assert np.array_equal(d, pd.numpy().astype(bool)) and np.array_equal(f1.cpu().numpy(), pf.numpy())
+        assert np.array_equal(r1.cpu().numpy(), pr.numpy())
+        ref = o1.cpu().numpy()[:, :nd]
+        if dtype == 'float32':
+            ref = ref.astype(np.float32)
+        live = ~d
+        assert np.array_equal(ref[live], po.numpy()[live]), t
+        if t > 0:
+            assert np.all(po.numpy()[d] == -7.0), t
+        n_done += int(d.sum())
+        ended |= d
+    assert n_done > 0
+
+
 def test_float32_observation_rows_are_the_float64_ones_rounded_once():
     """ppn_step_host_f32 (VecRunEnv.step_pinned(obs_dtype=float32)): same trajectory, every observation value equal to the
     float64 one narrowed to float32 -- nothing else changes (rewards, done, flags stay float64 / integer)."""
