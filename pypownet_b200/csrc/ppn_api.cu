@@ -1031,7 +1031,11 @@ static int ensure_staging(ppn_env* env) {
     CK(cudaMemset(env->d_row_flag, 0, B * sizeof(unsigned)));
     CK(cudaHostAlloc(&env->d_drain_err, sizeof(int), cudaHostAllocMapped));   // read by the host after every step: no copy
     *env->d_drain_err = 0;
-    CK(cudaStreamCreateWithFlags(&env->drain_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;   // "greatest" priority is the numerically lowest
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&env->drain_stream, cudaStreamNonBlocking, hi));
+    }
     // two chunks measured best on B200 (every chunk ends with its own slowest env, so more chunks overlap no more copy
     // time and only add launches); PPN_HOST_CHUNKS overrides the count
     int n = B >= 1024 ? 2 : 1;
@@ -1047,10 +1051,10 @@ static int ensure_staging(ppn_env* env) {
 // ---- drain kernel of the zero-copy host step.  A step CTA that stores its observation row straight into host memory holds
 // its SM slot until PCIe has accepted the row, so the burst of the first wave (every env of a small grid finishes within
 // ~100 us) delays the second wave by the time the link needs for it.  Instead the step kernel writes the row to device memory,
-// release-stores the row's flag and retires; the few warps of this kernel -- launched BEFORE the step kernel on a stream of
-// their own, so they are resident from the start -- poll the flags of their rows and move every finished row to the host
-// while the other envs still iterate.  The step kernel never waits for this one, so there is no deadlock in either launch order;
-// a spin limit (about two seconds) turns a step kernel that never ran into an error instead of a hang.
+// release-stores the row's flag and retires; the few warps of this kernel -- launched right after the step kernel on a
+// high-priority stream of their own -- poll the flags of their rows and move every finished row to the host while the other
+// envs still iterate.  The step kernel never waits for this one, so there is no deadlock; a spin limit (about two seconds)
+// turns a step kernel that hangs into an error instead of a second hang.
 #define PPN_DRAIN_MAXJ 4   // rows a lane watches at most
 __global__ void __launch_bounds__(1024) ppn_obs_drain_kernel(const unsigned long long* __restrict__ stage, long long stage_stride8,
                                                             unsigned long long* __restrict__ host, long long host_stride8, int n_rows,
@@ -1189,24 +1193,26 @@ static int step_host_impl(ppn_env* env, const uint8_t* act_host, double* obs_hos
             const bool drain = dev[0] && (drain_env ? atoi(drain_env) != 0 : row_bytes <= 4096) && (row_bytes % 8) == 0 &&
                                (f32 ? (obs_stride % 2) == 0 : true);
             if (drain) {
-                const int n8 = (int)(row_bytes / 8);
-                const long long ss8 = (long long)OD * (f32 ? 4 : 8) / 8, hs8 = obs_stride * (f32 ? 4 : 8) / 8;
-                // 64 rows per warp, 4 warps per CTA measured best on B200 (more, or larger, drain CTAs slow the step kernel down)
-                static const int rpw = []{ const char* v = getenv("PPN_DRAIN_ROWS"); int r = v ? atoi(v) : 64; return r < 1 ? 1 : (r > 32 * PPN_DRAIN_MAXJ ? 32 * PPN_DRAIN_MAXJ : r); }();
-                static const int blk = []{ const char* v = getenv("PPN_DRAIN_BLOCK"); int r = v ? atoi(v) : 128; return r < 32 ? 32 : (r > 1024 ? 1024 : (r & ~31)); }();
-                const int warps = ((int)B + rpw - 1) / rpw, wpb = blk / 32;
                 env->epoch = (env->epoch + 1) & 0x7fffffffu;
                 if (env->epoch == 0) env->epoch = 1;
+                a.obs = env->d_obs; a.obs_stride = (long long)OD; a.row_flag = env->d_row_flag; a.epoch = env->epoch;
+            }
+            rc = launch(env, a, s);
+            if (rc) return rc;
+            if (drain) {
+                // AFTER the step kernel, on a stream of the highest priority: its CTAs take the first SM slots the step kernel
+                // frees (about when the first rows are ready).  In this order a tool that serialises kernels (ncu, the sanitizer,
+                // CUDA_LAUNCH_BLOCKING) only loses the overlap; the other order would spin until the limit there.
+                const int n8 = (int)(row_bytes / 8);
+                const long long ss8 = (long long)OD * (f32 ? 4 : 8) / 8, hs8 = obs_stride * (f32 ? 4 : 8) / 8;
+                // 128 rows per warp, 4 warps per CTA measured best on B200 (more, or larger, drain CTAs slow the step kernel down)
+                static const int rpw = []{ const char* v = getenv("PPN_DRAIN_ROWS"); int r = v ? atoi(v) : 128; return r < 1 ? 1 : (r > 32 * PPN_DRAIN_MAXJ ? 32 * PPN_DRAIN_MAXJ : r); }();
+                static const int blk = []{ const char* v = getenv("PPN_DRAIN_BLOCK"); int r = v ? atoi(v) : 128; return r < 32 ? 32 : (r > 1024 ? 1024 : (r & ~31)); }();
+                const int warps = ((int)B + rpw - 1) / rpw, wpb = blk / 32;
                 ppn_obs_drain_kernel<<<(warps + wpb - 1) / wpb, blk, 0, env->drain_stream>>>(
                     reinterpret_cast<const unsigned long long*>(env->d_obs), ss8, reinterpret_cast<unsigned long long*>(dev[0]), hs8, (int)B,
                     n8, env->d_row_flag, env->epoch, warps, env->d_drain_err);
                 CK(cudaGetLastError());
-                a.obs = env->d_obs; a.obs_stride = (long long)OD; a.row_flag = env->d_row_flag; a.epoch = env->epoch;
-            }
-            rc = launch(env, a, s);
-            if (rc) {
-                if (drain) cudaStreamSynchronize(env->drain_stream);   // gives up after its spin limit
-                return rc;
             }
             CK(cudaStreamSynchronize(s));
             if (drain) {

@@ -9,8 +9,10 @@ d=json.loads(open('$OUT/tmp.json').read().strip().splitlines()[-1])
 print('$1 x $2 $3 $5 [$6]: kernel ms %.4f value %.3fM | e2e %.3fM (%.4f ms/step) e2e_f32 %.3fM'%(d['ms_per_step'],d['value']/1e6,d['e2e']['value']/1e6,1e3*$2/d['e2e']['value'],d['config']['e2e_float32_observations']['value']/1e6))
 PY
 }
-PPN_HOST_DRAIN=1 PPN_DRAIN_DEBUG=1 run case14 4096 nothing 100 "" "staging + flags, no drain kernel"
-PPN_HOST_DRAIN=1 run case14 4096 nothing 100 "" "drain"
-PPN_HOST_DRAIN=1 PPN_DRAIN_DEBUG=1 timeout 300 python tools/e2e_breakdown.py case14 4096 2>&1 | grep -v stride | tail -7
-PPN_HOST_DRAIN=1 timeout 300 python tools/e2e_breakdown.py case14 4096 2>&1 | grep -v stride | tail -7
+PPN_HOST_DRAIN=0 run case14 4096 nothing 100 "" "no drain"
+run case14 4096 nothing 100 "" "drain after the step kernel, priority stream"
+run case14 4096 random 100 "" "drain after the step kernel, priority stream"
+PPN_DRAIN_ROWS=32 run case14 4096 nothing 100 "" "drain 32 rows/warp"
+PPN_DRAIN_ROWS=128 run case14 4096 nothing 100 "" "drain 128 rows/warp"
+CUDA_LAUNCH_BLOCKING=1 run case14 4096 nothing 30 "" "kernels serialised (CUDA_LAUNCH_BLOCKING=1)"
 tail -3 $OUT/bench_drain.err
