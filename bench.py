@@ -366,6 +366,8 @@ def measure(ctx, grid, envs, agent, cascade, steps, warmup, with_e2e=True, sampl
     # while step t computes.  No collective between two steps: ranks never run in lock-step.
     pg = sharding.PeerGather(env, rank, world, ring=16) if world > 1 else None   # 16 slots: a rank may run 16 steps ahead
     tstep = [0]
+    if os.environ.get('PPN_BENCH_PG', '') == 'none':   # analysis only: no result gather at all
+        pg = None
 
     def one_step():
         t = tstep[0]

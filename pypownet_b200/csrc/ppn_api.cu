@@ -1329,13 +1329,15 @@ __global__ void ppn_peer_signal_kernel(unsigned long long* flag, unsigned long l
 
 __global__ void ppn_peer_wait_kernel(const unsigned long long* flags, int n, unsigned long long value) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        // relaxed polls with a long sleep, one acquire fence at the end: the warp shares its SM with step CTAs
         unsigned long long v;
         while (true) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + i) : "memory");
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + i) : "memory");
             if (v >= value) break;
-            __nanosleep(500);
+            __nanosleep(4000);
         }
     }
+    __threadfence_system();
 }
 
 extern "C" int ppn_peer_signal(int device, uint64_t* flag_dev, uint64_t value, void* stream) {
