@@ -187,10 +187,13 @@ int ppn_peer_signal(int device, uint64_t* flag_dev, uint64_t value, void* stream
 int ppn_peer_wait(int device, const uint64_t* flags_dev, int n, uint64_t value, void* stream);
 int ppn_peer_read(int device, void* host_dst, const void* dev_src, uint64_t bytes, void* stream);
 
-/* Host-buffer form of ppn_step (what a host-side agent calls, RunEnv.step semantics, environment.py:848-866): the batch
- * is cut into chunks, each chunk runs  actions H2D -> step kernel -> results D2H  on its own stream so that copies overlap
- * the kernels of the other chunks; returns when every result is in the host buffers.  Page-locked buffers
- * (cudaMallocHost / cudaHostRegister / torch pin_memory) are used in place, pageable ones are staged.  act_host NULL =
+/* Host-buffer form of ppn_step (what a host-side agent calls, RunEnv.step semantics, environment.py:848-866); returns
+ * when every result is in the host buffers.  When every result buffer is page-locked (cudaMallocHost / cudaHostRegister /
+ * torch pin_memory) there is ONE launch and no copy: the step kernel writes rewards / done / flags straight into host
+ * memory, and the observation rows either the same way (rows above 4 KB) or through a device buffer that a small drain
+ * kernel empties into the host buffer while the other envs still iterate (small rows: DESIGN.md section 5).  Otherwise the
+ * batch is cut into chunks, each chunk runs  actions H2D -> step kernel -> results D2H  on its own stream so that copies
+ * overlap the kernels of the other chunks; pageable buffers are staged.  act_host NULL =
  * do-nothing; obs_host NULL = no observation.  Without auto_reset the observation rows of envs that ended stay untouched
  * (the reference returns None).  Work enqueued earlier through the device-pointer calls is synchronised first. */
 int ppn_step_host(ppn_env* env, const uint8_t* act_host, double* obs_host, int64_t obs_stride, double* reward_host,
