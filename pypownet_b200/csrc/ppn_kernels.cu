@@ -234,32 +234,74 @@ __device__ __forceinline__ void sts64(unsigned a, double v) {
 // rank-1 update runs on registers.  `i` = row of this lane, `nsteps` is uniform over `syncmask` (max n of the
 // matrices inverted side by side), `piv_s` = NR doubles per matrix.  Same operation order as gj_invert.
 // NR = 16: pivot steps fully unrolled (static register indices, no select chains); two matrices fit one warp.
+// Eight consecutive doubles from a 16-byte aligned shared address in ONE asm statement: every load has registers of its
+// own and they issue back to back (separate volatile loads keep their program order and end up sharing one register
+// pair, i.e. a load -> FMA -> load chain of ~35 cycles per element: it was most of a pivot step)
+__device__ __forceinline__ void lds_8(unsigned a, double (&p)[8]) {
+    asm volatile(
+        "ld.shared.v2.f64 {%0, %1}, [%8];\n\t"
+        "ld.shared.v2.f64 {%2, %3}, [%8+16];\n\t"
+        "ld.shared.v2.f64 {%4, %5}, [%8+32];\n\t"
+        "ld.shared.v2.f64 {%6, %7}, [%8+48];\n\t"
+        : "=d"(p[0]), "=d"(p[1]), "=d"(p[2]), "=d"(p[3]), "=d"(p[4]), "=d"(p[5]), "=d"(p[6]), "=d"(p[7])
+        : "r"(a));
+}
+
+// 1/a without the special-case branch of __drcp_rn (pivots are ordinary numbers; a zero pivot still gives inf/NaN, i.e.
+// "diverging"): hardware seed + the same two refinement steps, within an ulp -- branch-free, so it interleaves with the
+// independent FMAs of the elimination
+__device__ __forceinline__ double rcp_plain(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    e = fma(e, e, e);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    return fma(x, e, x);
+}
+
 template <int NR>
 __device__ __forceinline__ void gj_rows_in_registers_impl(unsigned m_s, int n, int ld, int i, int nsteps, unsigned piv_s,
                                                           unsigned syncmask) {
+    static_assert(NR % 8 == 0, "rows are read eight doubles at a time");
     double row[NR];
     const bool mine = i < n;
+    piv_s = (piv_s + 15u) & ~15u;   // the pivot row buffer holds NR + 1 doubles
 #pragma unroll
     for (int j = 0; j < NR; j++) row[j] = (mine && j < n) ? lds64(m_s + 8u * (unsigned)(i * ld + j)) : 0.0;
+    // The reciprocal of a pivot is the other long chain of a step: every lane updates the column of the NEXT pivot first
+    // and starts that reciprocal at once (only lane k+1's is used), so it overlaps the rest of the elimination; the owner
+    // publishes its row already scaled and the others eliminate with their plain entry.
+    double pinv = rcp_plain(row[0]);
 #pragma unroll
     for (int k = 0; k < NR; k++) {
         if (k < nsteps) {
-            if (mine && i == k) {
+            const bool act = mine && k < n;
+            if (act && i == k) {
 #pragma unroll
-                for (int j = 0; j < NR; j++) sts64(piv_s + 8u * j, row[j]);
+                for (int j = 0; j < NR; j++) {
+                    row[j] = (j == k) ? pinv : row[j] * pinv;
+                    sts64(piv_s + 8u * j, row[j]);
+                }
             }
             __syncwarp(syncmask);
-            if (mine && k < n) {
-                const double p = 1.0 / lds64(piv_s + 8u * k);
-                if (i == k) {
+            if (act && i != k) {
+                const double ci = row[k];
+                row[k] = 0.0;   // becomes -ci * pinv below
+                constexpr int NBATCH = NR / 8;
+                const int first = (k + 1 < NR) ? (k + 1) / 8 : 0;   // the batch that holds the next pivot's column goes first
 #pragma unroll
-                    for (int j = 0; j < NR; j++) row[j] = (j == k) ? p : row[j] * p;
-                } else {
-                    const double ci = row[k] * p;
+                for (int bb = 0; bb < NBATCH; bb++) {
+                    const int b8 = (first + bb) % NBATCH;
+                    double pv[8];
+                    lds_8(piv_s + 64u * b8, pv);
+                    if (bb == 0 && k + 1 < NR) {
+                        row[k + 1] = fma(-ci, pv[(k + 1) % 8], row[k + 1]);
+                        pinv = rcp_plain(row[k + 1]);
+                    }
 #pragma unroll
-                    for (int j = 0; j < NR; j++)
-                        if (j != k) row[j] = fma(-ci, lds64(piv_s + 8u * j), row[j]);
-                    row[k] = -ci;
+                    for (int q = 0; q < 8; q++)
+                        if (!(bb == 0 && k + 1 < NR && q == (k + 1) % 8)) row[8 * b8 + q] = fma(-ci, pv[q], row[8 * b8 + q]);
                 }
             }
             __syncwarp(syncmask);
@@ -540,7 +582,7 @@ template <int TPE> __device__ __noinline__ void hyb_invert2(double* Z1, double* 
     if (nt <= 24) {
         // small blocks: one WARP per matrix with a row per lane in registers (pivot row through a 24-double shared buffer,
         // __syncwarp only) -- no CTA barrier per pivot; measured on IEEE-118 (17 rows): 29 k cycles with the tiled version
-        if (tid < 64) gj24_rows_in_registers(saddr(tid < 32 ? Z1 : Z2), nt, ldz, tid & 31, saddr(buf) + (tid < 32 ? 0u : 8u * 24u));
+        if (tid < 64) gj24_rows_in_registers(saddr(tid < 32 ? Z1 : Z2), nt, ldz, tid & 31, saddr(buf) + (tid < 32 ? 0u : 8u * 26u));   // 25 doubles each after the 16-byte alignment
         __syncthreads();
         return;
     }
@@ -1624,7 +1666,7 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                 PPN_TICK(8);
                 if (solve_mode) sp_recip<TPE>(*sp, f1, f2, true, tid, mask);
                 else sp_invert<TPE>(*sp, f1, f2, e.busp(), e.busq(), M1, M2, n1, n2, ld1, ld2, tid, mask);
-            } else if (TPE == 32 && SMEM && n1 <= 16 && n2 <= 16) {
+            } else if (TPE == 32 && SMEM && n1 <= 16 && n2 <= 16 && NB >= 18) {   // the pivot buffers (ydr | ydi) hold 17 doubles each
                 // both inverses at once: lanes 0-15 hold the rows of B', lanes 16-31 those of B''
                 const int hf = tid >> 4;
                 gj16_rows_in_registers(saddr(hf ? M2 : M1), hf ? n2 : n1, hf ? ld2 : ld1, tid & 15,
