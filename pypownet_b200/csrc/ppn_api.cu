@@ -148,6 +148,14 @@ static void build_warp_schedule(SparseHost& h, int cut) {
         for (int q = 0; q < st.maxcnt; q++)
             for (int l = 0; l < 32; l++) ent.push_back(q < (int)st.ent[l].size() ? (unsigned short)st.ent[l][q] : (unsigned short)0xffff);
     }
+    if (getenv("PPN_DEBUG_SCHED")) {
+        fprintf(stderr, "[ppn] one-warp solve schedule: n %d, top block %d rows, %zu forward + %zu backward steps\n", n, nt, fwd.size(), bwd.size());
+        for (const Step& st : all) {
+            int tot = 0;
+            for (int l = 0; l < 32; l++) tot += (int)st.ent[l].size();
+            fprintf(stderr, "[ppn]   rows %3d..%3d  longest row %2d entries, %3d entries in all\n", st.row0, st.row0 + st.rows - 1, st.maxcnt, tot);
+        }
+    }
     h.wsched.push_back((int)fwd.size());
     h.wsched.push_back((int)bwd.size());
     h.wsched.insert(h.wsched.end(), hdr.begin(), hdr.end());
@@ -281,10 +289,12 @@ static void build_sparse(int S, int N, const int* lor, const int* lex, const std
 }
 
 // hybrid cut: the lowest level from which at most cut_rows rows remain (at least one level stays sparse when there is one)
-static int choose_cut(const SparseHost& h, int cut_rows = 20) {
+static int choose_cut(const SparseHost& h, int cut_rows = 24) {
     // cut_rows: measured on B200 for IEEE-118 -- 256-thread CTAs, two per SM: 12 / 20 / 28 / 40 rows give 1.60 / 1.62 /
-    // 1.72 / 1.67 M env-steps/s; 128-thread CTAs, three per SM (the default): 12 / 20 rows give 1.99 / 2.14 M (28 rows
-    // no longer fit three CTAs).  At most 40: hyb_invert2 keeps a 5 x 5 tile per thread on an 8 x 8 thread grid.
+    // 1.72 / 1.67 M env-steps/s; 128-thread CTAs, three per SM (the default): 12 / 20 rows gave 1.99 / 2.14 M in round 1.
+    // With the warp-synchronous inverse of blocks of <= 24 rows (gj24_rows_in_registers) the optimum moved up: final
+    // round-2 kernels, a top block of 17 / 22 / 28 rows: 3.39 / 3.19 / 4.36 ms per 8 192-env step (28 rows: tiled
+    // inverse, and no longer three CTAs per SM).  At most 40: hyb_invert2 keeps a 5 x 5 tile per thread on an 8 x 8 grid.
     int cut = h.n_lev > 1 ? 1 : 0;
     if (const char* v = getenv("PPN_CUT_ROWS")) { cut_rows = atoi(v); if (cut_rows > 40) cut_rows = 40; if (cut_rows < 1) cut_rows = 1; }
     while (cut < h.n_lev - 1 && h.n - h.lev_rows_ptr[cut] > cut_rows) cut++;
