@@ -185,10 +185,13 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 5.0:      # up and sampling before anything is timed
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -388,6 +391,10 @@ def measure(ctx, grid, envs, agent, cascade, steps, warmup, with_e2e=True, sampl
             pg.collect(tstep[0] - 1)
             torch.cuda.current_stream().wait_stream(pg.side)
 
+    if sampler:
+        # before the warm-up steps: launching nvidia-smi (fork + NVML start-up) stalls this process and the GPU's driver for
+        # milliseconds -- inside the timed loop that was one 1-5 ms step on rank 0 (profiles/r2_scaling.txt, visit r2p)
+        sampler.start()
     warm = max(warmup, 3)
     for _ in range(warm):
         one_step()
@@ -398,8 +405,6 @@ def measure(ctx, grid, envs, agent, cascade, steps, warmup, with_e2e=True, sampl
     torch.cuda.synchronize()
     c0 = env.counters()
     ctx.barrier()
-    if sampler:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     n_done = torch.zeros((), dtype=torch.int64, device=dev)
     wall0 = time.perf_counter()
