@@ -1544,8 +1544,21 @@ __device__ __forceinline__ bool ac_solve(Env<TPE, D>& e, const PpnDevCase& c, co
                 const int b = tid + r * TPE;
                 if (half & 1) {   // P iteration: Va[pvpq] -= B'^-1 P
                     if (t == PPN_BT_PV || t == PPN_BT_PQ) {
-                        r_va[r] -= solve_mode ? e.P()[r_ip[r]] : row_dot(M1 + r_ip[r] * ld1, e.P(), n1);
-                        sincos(r_va[r], &r_sn[r], &r_cs[r]);
+                        const double d = solve_mode ? e.P()[r_ip[r]] : row_dot(M1 + r_ip[r] * ld1, e.P(), n1);
+                        r_va[r] -= d;
+                        if (fabs(d) < 0.03125) {
+                            // small step (every iteration but the first ones): rotate the unit phasor by -d with the Taylor
+                            // polynomials of sin d and cos d (next terms d^9/9!, d^10/10! < 1e-19) instead of a full
+                            // sincos of the new angle -- a quarter of its instructions on the dependent path
+                            const double d2 = d * d;
+                            const double sd = d * fma(d2, fma(d2, fma(d2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), 1.0);
+                            const double cd = fma(d2, fma(d2, fma(d2, fma(d2, 1.0 / 40320.0, -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
+                            const double c0 = r_cs[r], s0 = r_sn[r];
+                            r_cs[r] = fma(c0, cd, s0 * sd);
+                            r_sn[r] = fma(s0, cd, -c0 * sd);
+                        } else {
+                            sincos(r_va[r], &r_sn[r], &r_cs[r]);
+                        }
                         reinterpret_cast<double2*>(e.vri())[b] = make_double2(r_vm[r] * r_cs[r], r_vm[r] * r_sn[r]);
                     }
                 } else if (t == PPN_BT_PQ) {   // Q iteration: Vm[pq] -= B''^-1 Q
