@@ -1072,18 +1072,21 @@ __global__ void __launch_bounds__(1024) ppn_obs_drain_kernel(const unsigned long
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (gw >= n_warps) return;
-    // lane i watches the flags of rows gw + (i + 32 j) * n_warps, j = 0 .. PPN_DRAIN_MAXJ-1.  Interleaved, because the rows that
-    // finish last (the last wave of step CTAs) are neighbours: contiguous ranges would leave that tail to a few warps
+    // The warp owns rows gw, gw + n_warps, gw + 2 n_warps, ...  Interleaved, because the rows that finish last (the last
+    // wave of step CTAs) are neighbours: contiguous ranges would leave that tail to a few warps.  It drains them in rounds
+    // of 32 * PPN_DRAIN_MAXJ rows (one round for the default 128 rows per warp; more only for very large batches, whose
+    // rows finish roughly in this order anyway): lane i watches the flags of rows gw + (i + 32 (jb + j)) * n_warps.
+    const bool v16 = ((stage_stride8 | host_stride8) & 1) == 0 && ((reinterpret_cast<size_t>(stage) | reinterpret_cast<size_t>(host)) & 15) == 0;
+    const int n16 = n8 >> 1;
+    const long long t0 = clock64();
+    for (int jb = 0; gw + (long long)(32 * jb) * n_warps < n_rows; jb += PPN_DRAIN_MAXJ) {
     unsigned pending[PPN_DRAIN_MAXJ];
     unsigned any = 0;
 #pragma unroll
     for (int j = 0; j < PPN_DRAIN_MAXJ; j++) {
-        pending[j] = __ballot_sync(0xffffffffu, gw + (long long)(lane + 32 * j) * n_warps < n_rows);
+        pending[j] = __ballot_sync(0xffffffffu, gw + (long long)(lane + 32 * (jb + j)) * n_warps < n_rows);
         any |= pending[j];
     }
-    const bool v16 = ((stage_stride8 | host_stride8) & 1) == 0 && ((reinterpret_cast<size_t>(stage) | reinterpret_cast<size_t>(host)) & 15) == 0;
-    const int n16 = n8 >> 1;
-    const long long t0 = clock64();
     while (any) {
         unsigned got = 0;
         any = 0;
@@ -1091,7 +1094,7 @@ __global__ void __launch_bounds__(1024) ppn_obs_drain_kernel(const unsigned long
         for (int j = 0; j < PPN_DRAIN_MAXJ; j++) {
             if (!pending[j]) continue;
             unsigned f = 0;
-            if ((pending[j] >> lane) & 1u) f = *reinterpret_cast<const volatile unsigned*>(flags + gw + (long long)(lane + 32 * j) * n_warps);
+            if ((pending[j] >> lane) & 1u) f = *reinterpret_cast<const volatile unsigned*>(flags + gw + (long long)(lane + 32 * (jb + j)) * n_warps);
             const bool here = ((pending[j] >> lane) & 1u) && (f & 0x7fffffffu) == epoch;
             const unsigned ready = __ballot_sync(0xffffffffu, here);
             unsigned copy = __ballot_sync(0xffffffffu, here && !(f & 0x80000000u));   // rows that carry an observation
@@ -1102,7 +1105,7 @@ __global__ void __launch_bounds__(1024) ppn_obs_drain_kernel(const unsigned long
             while (copy) {
                 const int i = __ffs(copy) - 1;
                 copy &= copy - 1;
-                const long long row = gw + (long long)(i + 32 * j) * n_warps;
+                const long long row = gw + (long long)(i + 32 * (jb + j)) * n_warps;
                 const unsigned long long* src = stage + row * stage_stride8;
                 unsigned long long* dst = host + row * host_stride8;
                 if (v16) {
@@ -1133,6 +1136,7 @@ __global__ void __launch_bounds__(1024) ppn_obs_drain_kernel(const unsigned long
             if (clock64() - t0 > 4000000000ll) { if (lane == 0) atomicExch(error, 1); return; }
             __nanosleep(500);
         }
+    }
     }
 }
 
@@ -1216,9 +1220,11 @@ static int step_host_impl(ppn_env* env, const uint8_t* act_host, double* obs_hos
                 const int n8 = (int)(row_bytes / 8);
                 const long long ss8 = (long long)OD * (f32 ? 4 : 8) / 8, hs8 = obs_stride * (f32 ? 4 : 8) / 8;
                 // 128 rows per warp, 4 warps per CTA measured best on B200 (more, or larger, drain CTAs slow the step kernel down)
-                static const int rpw = []{ const char* v = getenv("PPN_DRAIN_ROWS"); int r = v ? atoi(v) : 128; return r < 1 ? 1 : (r > 32 * PPN_DRAIN_MAXJ ? 32 * PPN_DRAIN_MAXJ : r); }();
+                static const int rpw = []{ const char* v = getenv("PPN_DRAIN_ROWS"); int r = v ? atoi(v) : 128; return r < 1 ? 1 : r; }();
                 static const int blk = []{ const char* v = getenv("PPN_DRAIN_BLOCK"); int r = v ? atoi(v) : 128; return r < 32 ? 32 : (r > 1024 ? 1024 : (r & ~31)); }();
-                const int warps = ((int)B + rpw - 1) / rpw, wpb = blk / 32;
+                int warps = ((int)B + rpw - 1) / rpw;
+                if (warps > 64) warps = 64;   // more drain CTAs take SM slots from the step kernel; each warp then drains in rounds
+                const int wpb = blk / 32;
                 ppn_obs_drain_kernel<<<(warps + wpb - 1) / wpb, blk, 0, env->drain_stream>>>(
                     reinterpret_cast<const unsigned long long*>(env->d_obs), ss8, reinterpret_cast<unsigned long long*>(dev[0]), hs8, (int)B,
                     n8, env->d_row_flag, env->epoch, warps, env->d_drain_err);

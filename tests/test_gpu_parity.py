@@ -270,6 +270,25 @@ def test_pinned_rows_with_and_without_the_drain_kernel(monkeypatch, drain, dtype
     assert n_done > 0
 
 
+def test_drain_kernel_rounds_on_a_large_batch(monkeypatch):
+    """More than 64 x 128 rows: the drain warps (at most 64) take their rows in rounds.  Same bits as the device entry point."""
+    monkeypatch.setenv('PPN_HOST_DRAIN', '1')
+    fx = Fixture('d14_ac_random')
+    B = 9000
+    rng = np.random.default_rng(4)
+    start_r = rng.integers(0, 100, size=B).astype(np.int32)
+    e1 = vec_env(fx, B, start_chronics=np.zeros(B, dtype=np.int32), start_rows=start_r)
+    e2 = vec_env(fx, B, start_chronics=np.zeros(B, dtype=np.int32), start_rows=start_r)
+    nd = fx.case.obs_dynamic_length
+    act = torch.zeros((B, fx.case.action_length), dtype=torch.uint8).pin_memory()
+    for t in range(4):
+        o1, r1, d1, f1 = e1.step(act.numpy(), auto_reset=True)
+        po, pr, pd, pf = e2.step_pinned(act, auto_reset=True)
+        assert np.array_equal(o1.cpu().numpy()[:, :nd], po.numpy()), t
+        assert np.array_equal(r1.cpu().numpy(), pr.numpy()) and np.array_equal(d1.cpu().numpy(), pd.numpy())
+        assert np.array_equal(f1.cpu().numpy(), pf.numpy())
+
+
 def test_float32_observation_rows_are_the_float64_ones_rounded_once():
     """ppn_step_host_f32 (VecRunEnv.step_pinned(obs_dtype=float32)): same trajectory, every observation value equal to the
     float64 one narrowed to float32 -- nothing else changes (rewards, done, flags stay float64 / integer)."""
