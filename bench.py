@@ -6,8 +6,12 @@ N=1 workload = BASELINE.json configs[1]: default14 AC, 4096 batched envs, do-not
 different chronics/rows, games that end are restarted in the same step (Runner semantics).  The reference's chronics
 do not travel with the repo: chronics are synthetic with the shipped ones' statistics (pypownet_b200/synthetic.py).
 A "step" is one env-step of every env of the batch (one fused kernel launch).  One JSON line on stdout (rank 0).
-`--impl reference` times the CPU restatement of the reference's path (oracle/flat.py, the reference package itself
-is not present on the GPU box) on all host cores for the same workload, on a bounded sample per step.
+`--impl reference` times the UNMODIFIED reference package (installed in baseline/_ref by tools/install_reference.sh; it
+travels with the snapshot) on all host cores for the same workload, on a bounded sample per step: one RunEnv per process
+on oracle/shims (PYPOWER / gym restated).  Without baseline/_ref -- or with PPN_CPU_BASELINE=port -- it times the numpy
+restatement of the same path (oracle/flat.py) and says kind "port".
+Other switches: --cascade (synthetic thermal limits that trip), --agent nothing|random, --no-secondary (only the primary
+workload), --no-cpu, --sharding spread|blocks|strided, --emulate-shard R/W, --profile-ranks FILE (per-rank table at N>1).
 """
 import argparse
 import json
@@ -224,7 +228,8 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------------------------------------- main
 def run_reference(args):
-    """CPU arm: oracle/flat.py (port of the reference's step path) on every host core, do-nothing agent."""
+    """CPU arm: the unmodified reference package (baseline/_ref) -- or, without it, oracle/flat.py -- on every host core,
+    do-nothing agent, a bounded sample of the workload per bench step."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
