@@ -47,6 +47,9 @@ SCENARIOS = {
     'd30_ac_random': (P + '/default30', 'case30', 'ab', 100, 120, 'random', 'soft', {}, True, 5),
     'd118_ac_nothing': (P + '/default118', 'case118', 'ab', 40, 50, 'nothing', 'soft', {}, False, 0),
     'd118_ac_random': (P + '/default118', 'case118', 'ab', 40, 50, 'random', 'soft', {}, False, 6),
+    # the shipped 600 A limits of default30 never trip; the synthetic limits of
+    # tools/make_cascade_limits.py (pypownet_b200/data/case30.json, imaps_cascade) make the cascading-failure loop fire
+    'd30_ac_cascade': (P + '/default30', 'case30', 'ab', 100, 150, 'nothing', 'soft', {'_imaps': 'case30'}, False, 0),
     # BASELINE.json configs[0]: default14 DC, do-nothing agent, 1000 timesteps, single env (chronic a rolls into b)
     'd14_dc_nothing_1000': (P + '/default14', 'case14', 'ab', None, 1000, 'nothing', 'soft', {'loadflow_mode': 'DC'},
                             False, 0),
@@ -72,7 +75,8 @@ def build_folder(src, chronics, rows, overrides, dst):
         shutil.copy(os.path.join(src, 'level0', f), os.path.join(dst, 'level0', f))
     with open(os.path.join(src, 'level0', 'configuration.yaml')) as f:
         cfg = yaml.safe_load(f)
-    cfg.update(overrides)
+    cfg.update({k: v for k, v in overrides.items() if not k.startswith('_')})
+    imaps = overrides.get('_imaps')          # thermal limits that replace the chronics' own (the cascade scenarios)
     with open(os.path.join(dst, 'level0', 'configuration.yaml'), 'w') as f:
         yaml.safe_dump(cfg, f)
     for ch in chronics:
@@ -82,6 +86,9 @@ def build_folder(src, chronics, rows, overrides, dst):
             with open(os.path.join(s, fn)) as f:
                 lines = f.read().splitlines()
             keep = lines if (rows is None or fn == '_N_imaps.csv') else lines[:rows + 1]
+            if fn == '_N_imaps.csv' and imaps is not None:
+                assert len(imaps) == len(lines[0].split(';'))
+                keep = [lines[0], ';'.join('%g' % v for v in imaps)]
             with open(os.path.join(d, fn), 'w') as f:
                 f.write('\n'.join(keep) + '\n')
     return cfg
@@ -151,6 +158,9 @@ def run(name):
     import logging
     logging.disable(logging.CRITICAL)
     src, casename, chronics, rows, n_steps, agent, mode, overrides, do_sim, seed = SCENARIOS[name]
+    if isinstance(overrides.get('_imaps'), str):
+        with open(os.path.join(ROOT, 'pypownet_b200', 'data', overrides['_imaps'] + '.json')) as f:
+            overrides = dict(overrides, _imaps=json.load(f)['imaps_cascade'])
     tmp = '/tmp/golden_envs/' + name
     cfgd = build_folder(src, chronics, rows, overrides, tmp)
     os.environ.pop('PYPOWNET_SHIM_PF_ALG', None)
