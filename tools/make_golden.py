@@ -50,6 +50,7 @@ SCENARIOS = {
     # the shipped 600 A limits of default30 never trip; the synthetic limits of
     # tools/make_cascade_limits.py (pypownet_b200/data/case30.json, imaps_cascade) make the cascading-failure loop fire
     'd30_ac_cascade': (P + '/default30', 'case30', 'ab', 100, 150, 'nothing', 'soft', {'_imaps': 'case30'}, False, 0),
+    'd118_ac_cascade': (P + '/default118', 'case118', 'ab', 40, 60, 'nothing', 'soft', {'_imaps': 'case118'}, False, 0),
     # BASELINE.json configs[0]: default14 DC, do-nothing agent, 1000 timesteps, single env (chronic a rolls into b)
     'd14_dc_nothing_1000': (P + '/default14', 'case14', 'ab', None, 1000, 'nothing', 'soft', {'loadflow_mode': 'DC'},
                             False, 0),
